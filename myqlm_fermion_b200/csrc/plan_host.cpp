@@ -1,0 +1,319 @@
+// Sweep planner (host).  See plan_host.h for the vocabulary.
+#include "plan_host.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+
+namespace qfe {
+
+namespace {
+
+inline int popc64(uint64_t v) { return __builtin_popcountll(v); }
+
+struct Group {
+    int32_t slot;
+    uint64_t x_lo;
+    int64_t tb;  // first term (index into the canonical term arrays)
+    int32_t nt;
+};
+
+// gather-form coefficient of term i: (H psi)[b] = sum_t cg_t (-1)^{|z_t & b|} psi[b ^ x_t]
+// cg = c_Y * (-i)^{|x&z|} * (-1)^{|z_hi & shard|}
+inline void gather_coeff(const TermView& t, int64_t i, int n_local, int shard, double& re, double& im) {
+    re = t.c[2 * i];
+    im = t.c[2 * i + 1];
+    switch (popc64(t.x[i] & t.z[i]) & 3) {
+        case 1: { double a = re; re = im; im = -a; break; }
+        case 2: re = -re; im = -im; break;
+        case 3: { double a = re; re = -im; im = a; break; }
+        default: break;
+    }
+    const uint64_t z_hi = n_local >= 64 ? 0 : (t.z[i] >> n_local);
+    if (popc64(z_hi & (uint64_t)shard) & 1) {
+        re = -re;
+        im = -im;
+    }
+}
+
+void finish_sweep_geometry(SweepHost& s, int n_local) {
+    const uint64_t all = n_local >= 64 ? ~uint64_t(0) : ((uint64_t(1) << n_local) - 1);
+    // free positions of L above the low bits, ascending -> spread tables
+    int pos[PLAN_MAX_TILE_BITS];
+    int np = 0;
+    for (int b = s.low_bits; b < n_local; ++b)
+        if ((s.tile_mask >> b) & 1) pos[np++] = b;
+    for (int tbl = 0; tbl < 2; ++tbl)
+        for (uint32_t v = 0; v < 64; ++v) {
+            uint64_t m = 0;
+            for (int i = 0; i < 6; ++i) {
+                int idx = tbl * 6 + i;
+                if (idx < np && ((v >> i) & 1)) m |= uint64_t(1) << pos[idx];
+            }
+            s.spread[tbl][v] = m;
+        }
+    // runs of the outer mask
+    const uint64_t outer = all & ~s.tile_mask;
+    s.n_runs = 0;
+    int b = 0;
+    while (b < n_local) {
+        if ((outer >> b) & 1) {
+            int e = b;
+            while (e < n_local && ((outer >> e) & 1)) ++e;
+            s.run_pos[s.n_runs] = (uint8_t)b;
+            s.run_len[s.n_runs] = (uint8_t)(e - b);
+            ++s.n_runs;
+            b = e;
+        } else {
+            ++b;
+        }
+    }
+    s.n_tiles = int64_t(1) << (n_local - s.k);
+}
+
+}  // namespace
+
+uint32_t compress_to_tile(const SweepHost& s, uint64_t mask) {
+    uint32_t out = (uint32_t)(mask & ((uint64_t(1) << s.low_bits) - 1));
+    int i = s.low_bits;
+    uint64_t rest = s.tile_mask >> s.low_bits << s.low_bits;
+    while (rest) {
+        int b = __builtin_ctzll(rest);
+        if ((mask >> b) & 1) out |= 1u << i;
+        ++i;
+        rest &= rest - 1;
+    }
+    return out;
+}
+
+uint64_t tile_base(const SweepHost& s, uint64_t tile) {
+    uint64_t base = 0;
+    for (int r = 0; r < s.n_runs; ++r) {
+        const uint64_t m = (uint64_t(1) << s.run_len[r]) - 1;
+        base |= (tile & m) << s.run_pos[r];
+        tile >>= s.run_len[r];
+    }
+    return base;
+}
+
+uint64_t tile_spread(const SweepHost& s, uint32_t j) {
+    const uint32_t lowmask = (1u << s.low_bits) - 1;
+    return (uint64_t)(j & lowmask) | s.spread[0][(j >> s.low_bits) & 63] | s.spread[1][(j >> (s.low_bits + 6)) & 63];
+}
+
+int build_plan(const TermView& t, int n_local, int shard, const PlanLimits& lim, PlanHost& out, const char** err) {
+    static const char* e_arg = "build_plan: bad geometry";
+    if (n_local < 0 || n_local > t.n || t.n > 64 || t.n - n_local > 30 || shard < 0 || (t.n - n_local < 31 && shard >= (1 << (t.n - n_local)))) {
+        if (err) *err = e_arg;
+        return 1;
+    }
+    if (lim.tile_bits > PLAN_MAX_TILE_BITS || lim.max_terms > 32767 || lim.max_terms < 1 || lim.max_groups < 1) {
+        if (err) *err = "build_plan: limits out of range";
+        return 1;
+    }
+    out = PlanHost();
+    out.n = t.n;
+    out.n_local = n_local;
+    out.shard = shard;
+    out.n_slots = t.n_slots;
+    const uint64_t lomask = n_local >= 64 ? ~uint64_t(0) : ((uint64_t(1) << n_local) - 1);
+
+    // terms: canonical set + one identity term per slot with a non-zero constant (it is just the
+    // (x=0, z=0) member of the diagonal group; contributes constant * <bra|ket>)
+    struct TRec {
+        int32_t slot;
+        uint64_t x, z;
+        double re, im;
+    };
+    std::vector<TRec> recs;
+    recs.reserve(t.T + t.n_slots);
+    {
+        int64_t i = 0;
+        for (int64_t s = 0; s < t.n_slots; ++s) {
+            if (t.constant && (t.constant[2 * s] != 0.0 || t.constant[2 * s + 1] != 0.0)) recs.push_back({(int32_t)s, 0, 0, t.constant[2 * s], t.constant[2 * s + 1]});
+            while (i < t.T && (t.owner ? t.owner[i] : 0) == s) {
+                TRec r;
+                r.slot = (int32_t)s;
+                r.x = t.x[i];
+                r.z = t.z[i];
+                gather_coeff(t, i, n_local, shard, r.re, r.im);
+                recs.push_back(r);
+                ++i;
+            }
+        }
+        if (i != t.T) {
+            if (err) *err = "build_plan: terms are not sorted by slot";
+            return 1;
+        }
+    }
+    const int64_t NT = (int64_t)recs.size();
+
+    // groups per class
+    std::map<int32_t, std::vector<Group>> by_class;
+    for (int64_t i = 0; i < NT;) {
+        int64_t j = i;
+        while (j < NT && recs[j].slot == recs[i].slot && recs[j].x == recs[i].x) ++j;
+        const int32_t x_hi = n_local >= 64 ? 0 : (int32_t)(recs[i].x >> n_local);
+        // split oversized groups: (W1 + W2) psi[b^x] = W1 psi[b^x] + W2 psi[b^x]
+        for (int64_t b = i; b < j; b += lim.max_terms) {
+            Group g;
+            g.slot = recs[i].slot;
+            g.x_lo = recs[i].x & lomask;
+            g.tb = b;
+            g.nt = (int32_t)std::min<int64_t>(lim.max_terms, j - b);
+            by_class[x_hi].push_back(g);
+        }
+        i = j;
+    }
+
+    const int k = std::min(n_local, lim.tile_bits);
+    out.k = k;
+    out.use_tiles = k >= PLAN_MIN_TILE_BITS;
+    const int low = std::min(PLAN_LOW_BITS, k);
+    const uint64_t lowmask = (uint64_t(1) << low) - 1;
+
+    for (auto& kv : by_class) {
+        ClassHost cls;
+        cls.x_hi = kv.first;
+        std::vector<Group>& groups = kv.second;
+        const int ci = (int)out.classes.size();
+
+        // ---- direct layout ----
+        cls.dterm_begin = (int64_t)out.d_x.size();
+        cls.dgroup_begin = (int32_t)out.dg_slot.size();
+        for (const Group& g : groups) {
+            out.dg_slot.push_back(g.slot);
+            out.dg_begin.push_back((int64_t)out.d_x.size());
+            for (int64_t i = g.tb; i < g.tb + g.nt; ++i) {
+                out.d_x.push_back(recs[i].x & lomask);
+                out.d_z.push_back(recs[i].z & lomask);
+                out.d_cre.push_back(recs[i].re);
+                out.d_cim.push_back(recs[i].im);
+            }
+        }
+        cls.dterm_end = (int64_t)out.d_x.size();
+        cls.dgroup_end = (int32_t)out.dg_slot.size();
+
+        // ---- tiled layout: greedy cover of the groups' x_lo by tile masks ----
+        cls.sweep_begin = (int32_t)out.sweeps.size();
+        if (out.use_tiles) {
+            const size_t ng = groups.size();
+            std::vector<uint64_t> need(ng);
+            std::vector<char> done(ng, 0);
+            size_t left = ng;
+            for (size_t g = 0; g < ng; ++g) need[g] = groups[g].x_lo & ~lowmask;
+            const int free_slots = k - low;
+            const double fbase = 8.0;
+            double fpow[PLAN_MAX_TILE_BITS + 2];
+            for (int m = 0; m <= PLAN_MAX_TILE_BITS + 1; ++m) fpow[m] = std::pow(fbase, -m);
+            // wide groups (more free bits than a tile has) can only be reached through a
+            // non-zero ket_xor; narrow ones are covered first with ket_xor = 0
+            while (left > 0) {
+                // seed: virtual all-zero mask while narrow groups remain, else the first wide group
+                uint64_t seed = 0;
+                bool have_narrow = false;
+                for (size_t g = 0; g < ng && !have_narrow; ++g)
+                    if (!done[g] && popc64(need[g]) <= free_slots) have_narrow = true;
+                if (!have_narrow) {
+                    for (size_t g = 0; g < ng; ++g)
+                        if (!done[g]) {
+                            seed = need[g];
+                            break;
+                        }
+                }
+                uint64_t L = lowmask;
+                if (n_local <= k) {
+                    L = lomask;
+                } else {
+                    for (int step = 0; step < free_slots; ++step) {
+                        const int cap = free_slots - step - 1;  // slots left after this pick
+                        double gain[64];
+                        for (int p = 0; p < 64; ++p) gain[p] = 0.0;
+                        for (size_t g = 0; g < ng; ++g) {
+                            if (done[g]) continue;
+                            uint64_t miss = (need[g] ^ seed) & ~L;
+                            const int m = popc64(miss);
+                            if (m == 0 || m - 1 > cap) continue;
+                            const double d = fpow[m - 1] - (m <= cap ? fpow[m] : 0.0);
+                            while (miss) {
+                                gain[__builtin_ctzll(miss)] += d;
+                                miss &= miss - 1;
+                            }
+                        }
+                        int best = -1;
+                        for (int p = low; p < n_local; ++p)
+                            if (!((L >> p) & 1) && (best < 0 || gain[p] > gain[best])) best = p;
+                        L |= uint64_t(1) << best;
+                    }
+                }
+                const uint64_t kxor = seed & ~L;
+                SweepHost s;
+                s.cls = ci;
+                s.k = k;
+                s.low_bits = low;
+                s.tile_mask = L;
+                s.ket_xor = kxor;
+                finish_sweep_geometry(s, n_local);
+                // take coverable groups in order until the staging capacity is reached
+                std::vector<size_t> take;
+                int64_t nterms = 0;
+                for (size_t g = 0; g < ng; ++g) {
+                    if (done[g] || ((need[g] & ~L) != kxor)) continue;
+                    if ((int)take.size() >= lim.max_groups || nterms + groups[g].nt > lim.max_terms) break;
+                    take.push_back(g);
+                    nterms += groups[g].nt;
+                }
+                // classify coefficients
+                bool cplx = false;
+                std::vector<char> imag(take.size(), 0);
+                for (size_t a = 0; a < take.size(); ++a) {
+                    const Group& g = groups[take[a]];
+                    bool all_re = true, all_im = true;
+                    for (int64_t i = g.tb; i < g.tb + g.nt; ++i) {
+                        if (recs[i].im != 0.0) all_re = false;
+                        if (recs[i].re != 0.0) all_im = false;
+                    }
+                    if (all_re)
+                        imag[a] = 0;
+                    else if (all_im)
+                        imag[a] = 1;
+                    else
+                        cplx = true;
+                }
+                s.complex_w = cplx;
+                s.group_begin = (int32_t)out.g_hdr.size();
+                s.term_begin = (int64_t)out.t_zl.size();
+                for (size_t a = 0; a < take.size(); ++a) {
+                    const Group& g = groups[take[a]];
+                    const uint32_t xl = compress_to_tile(s, g.x_lo);
+                    const bool im_flag = !cplx && imag[a];
+                    out.g_hdr.push_back(xl | ((uint32_t)g.nt << 16) | (im_flag ? 0x80000000u : 0u));
+                    out.g_slot.push_back(g.slot);
+                    for (int64_t i = g.tb; i < g.tb + g.nt; ++i) {
+                        const uint64_t z_lo = recs[i].z & lomask;
+                        out.t_zl.push_back(compress_to_tile(s, z_lo & L));
+                        out.t_zo.push_back(z_lo & ~L);
+                        out.t_cre.push_back(im_flag ? recs[i].im : recs[i].re);
+                        out.t_cim.push_back(im_flag ? 0.0 : recs[i].im);
+                    }
+                    done[take[a]] = 1;
+                    --left;
+                }
+                s.group_end = (int32_t)out.g_hdr.size();
+                s.term_end = (int64_t)out.t_zl.size();
+                out.sweeps.push_back(s);
+                if (take.empty()) {  // cannot happen: every group fits an empty sweep
+                    if (err) *err = "build_plan: internal error (empty sweep)";
+                    return 1;
+                }
+            }
+        }
+        cls.sweep_end = (int32_t)out.sweeps.size();
+        out.classes.push_back(cls);
+    }
+    out.dg_begin.push_back((int64_t)out.d_x.size());
+    return 0;
+}
+
+}  // namespace qfe

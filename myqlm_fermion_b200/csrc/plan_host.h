@@ -1,0 +1,91 @@
+// Host-side sweep planner of kernel (2).  Pure C++ (no CUDA) so that the planner's output can be
+// interpreted on the CPU by the test-only emulator in tests/csrc/.
+//
+// A *group* is the set of terms of one operator slot that share an X mask.  Groups whose X mask
+// has high part x_hi (the bits above n_local) form *class* x_hi: they read the ket shard of rank
+// shard^x_hi.  Inside a class the groups are covered by *sweeps*: a sweep fixes a set L of k
+// shard-local bit positions (the low ``low_bits`` positions plus k-low_bits free ones); every
+// group of the sweep has x_lo = ket_xor + (bits inside L) with one ket_xor outside L, so a CTA that stages the 2^k amplitudes {base | spread(j)}
+// of one *tile* in shared memory finds every XOR partner in that tile.  One sweep = one kernel
+// launch = one pass over the shard in HBM, evaluating all its groups.
+#pragma once
+
+#include <cstdint>
+#include <vector>
+
+namespace qfe {
+
+struct TermView {
+    int n = 0;
+    int64_t T = 0;
+    const uint64_t* x = nullptr;
+    const uint64_t* z = nullptr;
+    const double* c = nullptr;  // Y-form (Term.coeff), interleaved complex
+    const int32_t* owner = nullptr;
+    int64_t n_slots = 1;
+    const double* constant = nullptr;  // 2*n_slots
+};
+
+constexpr int PLAN_MAX_TILE_BITS = 15;
+constexpr int PLAN_MIN_TILE_BITS = 8;   // below this the direct kernel is used
+constexpr int PLAN_MAX_RUNS = 24;
+constexpr int PLAN_LOW_BITS = 3;        // 8 amplitudes = 128 B (c128) contiguous per gather segment
+
+struct PlanLimits {
+    int tile_bits = 13;
+    int max_terms = 4096;  // per sweep (shared-memory staging capacity)
+    int max_groups = 1024;
+};
+
+struct SweepHost {
+    int cls = 0;            // index into PlanHost::classes
+    int k = 0;              // tile bits
+    int low_bits = 0;       // identity-mapped low bits
+    uint64_t tile_mask = 0; // L
+    uint64_t ket_xor = 0;   // shard-local bits outside L shared by every X mask of the sweep: ket tile = base ^ ket_xor
+    int n_runs = 0;         // runs of the outer mask (shard bits outside L), LSB first
+    uint8_t run_pos[PLAN_MAX_RUNS] = {0};
+    uint8_t run_len[PLAN_MAX_RUNS] = {0};
+    uint64_t spread[2][64] = {{0}};  // tile-local bits [low, low+6) and [low+6, low+12) -> shard positions
+    int64_t n_tiles = 0;
+    int32_t group_begin = 0, group_end = 0;
+    int64_t term_begin = 0, term_end = 0;
+    bool complex_w = false;  // some group mixes real and imaginary gather coefficients
+};
+
+struct ClassHost {
+    int32_t x_hi = 0;
+    int32_t sweep_begin = 0, sweep_end = 0;
+    int64_t dterm_begin = 0, dterm_end = 0;    // direct-kernel term range
+    int32_t dgroup_begin = 0, dgroup_end = 0;  // direct-kernel group range
+};
+
+struct PlanHost {
+    int n = 0, n_local = 0, shard = 0, k = 0;
+    int64_t n_slots = 1;
+    bool use_tiles = false;
+    std::vector<ClassHost> classes;  // ascending x_hi
+    std::vector<SweepHost> sweeps;
+    // tiled layout (sweep order)
+    std::vector<uint32_t> g_hdr;   // xl (bits 0..15) | nterms (bits 16..30) | imag flag (bit 31)
+    std::vector<int32_t> g_slot;
+    std::vector<uint32_t> t_zl;    // tile-local z mask
+    std::vector<uint64_t> t_zo;    // shard-local z bits outside the tile
+    std::vector<double> t_cre, t_cim;  // gather-form coefficients, rank sign folded; imag groups keep Im in t_cre
+    // direct layout (class order, original term order inside a class)
+    std::vector<uint64_t> d_x, d_z;  // shard-local masks
+    std::vector<double> d_cre, d_cim;
+    std::vector<int32_t> dg_slot;      // per direct group
+    std::vector<int64_t> dg_begin;     // per direct group: first term (size n_dgroups+1)
+};
+
+// returns 0 on success, nonzero with *err set otherwise
+int build_plan(const TermView& t, int n_local, int shard, const PlanLimits& lim, PlanHost& out, const char** err);
+
+// tile-local compression of a mask that lies inside the sweep's tile mask
+uint32_t compress_to_tile(const SweepHost& s, uint64_t mask);
+// shard position of tile-local index j for tile number `tile`
+uint64_t tile_base(const SweepHost& s, uint64_t tile);
+uint64_t tile_spread(const SweepHost& s, uint32_t j);
+
+}  // namespace qfe

@@ -1,0 +1,795 @@
+// Kernel (2): matrix-free Pauli-sum apply / expectation on a statevector shard.
+//
+// Replaces SpinHamiltonian.get_matrix (/root/reference/qat/fermion/hamiltonians.py:163-250) plus the
+// matrix-vector products at the reference's call sites.  The reference materialises a 2^n x 2^n
+// matrix; here every launch ("sweep") streams the shard through shared memory once:
+//
+//   * a CTA stages one *tile* -- 2^k amplitudes whose index differs only in the k bit positions
+//     the sweep's X masks live in -- with coalesced 128-bit loads (128 B contiguous segments);
+//   * every XOR partner psi[b ^ x] of every term group of the sweep is then a shared-memory read
+//     (conflict-free: a warp reads a permutation of 32 consecutive 16 B words);
+//   * signs come from popc parity: the part of z inside the tile is one __popc per (term, thread)
+//     shared by the thread's R register-blocked rows; the part outside the tile is folded into the
+//     coefficient once per tile;
+//   * W_x(b) = sum_t c_t (-1)^{|z_t & b|} costs one 32-bit select (sign bit of the high word) and
+//     one DADD per (term, amplitude);
+//   * the expectation is reduced by warp shuffles, then per block, then by a fixed-order reduce
+//     kernel (bit-reproducible).
+// No tensor cores: this is an XOR-gather with +-1 weights, not a dense contraction.
+#include <algorithm>
+#include <cstdlib>
+
+#include "common.cuh"
+#include "plan_host.h"
+
+namespace qfe {
+
+constexpr int NT = 512;           // threads per CTA of the tile kernel
+constexpr int NW = NT / 32;
+constexpr int RBITS = 3;          // register-blocked rows per thread: R = 8
+static_assert(PLAN_MIN_TILE_BITS == 5 + RBITS, "a tile must hold at least one full warp row block");
+
+enum { MODE_EXPECT = 0, MODE_APPLY = 1, MODE_BATCH = 2 };
+
+template <typename real_t> struct CplxOf;
+template <> struct CplxOf<double> { using type = double2; };
+template <> struct CplxOf<float> { using type = float2; };
+
+struct SweepArgs {
+    const void* ket;
+    const void* bra;
+    void* out_vec;
+    double2* partials;
+    const uint32_t* g_hdr;
+    const uint32_t* t_zl;
+    const uint64_t* t_zo;
+    const double* t_cre;
+    const double* t_cim;
+    int n_groups, n_terms;
+    int k, low_bits, n_runs;
+    int same_tile, accumulate;
+    unsigned long long n_tiles;
+    unsigned long long ket_xor;
+    uint8_t run_pos[PLAN_MAX_RUNS];
+    uint8_t run_len[PLAN_MAX_RUNS];
+    uint64_t spread[128];
+};
+
+struct SmemLayout {
+    size_t cre, cim, zp, hdr, spread, acc, red, total;
+};
+
+__host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~size_t(15); }
+
+__host__ __device__ inline SmemLayout smem_layout(int k, int n_terms, int n_groups, size_t real_bytes, bool cplx, bool batch) {
+    SmemLayout L;
+    size_t off = (size_t(1) << k) * 2 * real_bytes;
+    L.cre = off;
+    off += align16((size_t)n_terms * real_bytes);
+    L.cim = off;
+    if (cplx) off += align16((size_t)n_terms * real_bytes);
+    L.zp = off;
+    off += align16((size_t)n_terms * 4);
+    L.hdr = off;
+    off += align16((size_t)n_groups * 4);
+    L.spread = off;
+    off += 128 * 8;
+    L.acc = off;
+    if (batch) off += (size_t)NW * n_groups * sizeof(double2);
+    L.red = off;
+    off += NW * sizeof(double2);
+    L.total = off;
+    return L;
+}
+
+__device__ __forceinline__ double2 block_reduce_sum(double2 v, double2* s_red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        v.x += __shfl_down_sync(0xffffffffu, v.x, d);
+        v.y += __shfl_down_sync(0xffffffffu, v.y, d);
+    }
+    __syncthreads();
+    if (lane == 0) s_red[warp] = v;
+    __syncthreads();
+    double2 r = make_double2(0.0, 0.0);
+    if (threadIdx.x == 0) {
+        const int nw = blockDim.x >> 5;
+        for (int w = 0; w < nw; ++w) {
+            r.x += s_red[w].x;
+            r.y += s_red[w].y;
+        }
+    }
+    return r;  // valid in thread 0
+}
+
+// streaming 128-bit / 64-bit loads that do not pollute L1
+__device__ __forceinline__ double2 ld_stream(const double2* p) {
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float2 ld_stream(const float2* p) {
+    float2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+
+// w += (flag ? -c : c).  -c differs from c only in the sign bit of its high word, so the select
+// is ONE 32-bit SEL on the high word (the plain C++ conditional costs two selects on the 64-bit sum).
+__device__ __forceinline__ void add_signed(double& w, double c, bool flag) {
+    const int hi = __double2hiint(c), lo = __double2loint(c);
+    w += __hiloint2double(flag ? (hi ^ (int)0x80000000) : hi, lo);
+}
+__device__ __forceinline__ void add_signed(float& w, float c, bool flag) {
+    w += __int_as_float(flag ? (__float_as_int(c) ^ (int)0x80000000) : __float_as_int(c));
+}
+
+template <typename real_t, int RB, bool CPLX, int MODE>
+__global__ void __launch_bounds__(NT, 1) tile_sweep_kernel(const __grid_constant__ SweepArgs a) {
+    using cplx_t = typename CplxOf<real_t>::type;
+    constexpr int R = 1 << RB;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int k = a.k;
+    const uint32_t tile_amps = 1u << k;
+    const int nT = a.n_terms, nG = a.n_groups;
+    const SmemLayout L = smem_layout(k, nT, nG, sizeof(real_t), CPLX, MODE == MODE_BATCH);
+    cplx_t* tile = reinterpret_cast<cplx_t*>(smem);
+    real_t* s_cre = reinterpret_cast<real_t*>(smem + L.cre);
+    real_t* s_cim = reinterpret_cast<real_t*>(smem + L.cim);
+    uint32_t* s_zp = reinterpret_cast<uint32_t*>(smem + L.zp);
+    uint32_t* s_hdr = reinterpret_cast<uint32_t*>(smem + L.hdr);
+    uint64_t* s_spread = reinterpret_cast<uint64_t*>(smem + L.spread);
+    double2* s_acc = reinterpret_cast<double2*>(smem + L.acc);
+    double2* s_red = reinterpret_cast<double2*>(smem + L.red);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const cplx_t* __restrict__ ket = reinterpret_cast<const cplx_t*>(a.ket);
+    const cplx_t* __restrict__ bra = reinterpret_cast<const cplx_t*>(a.bra);
+    cplx_t* __restrict__ yout = reinterpret_cast<cplx_t*>(a.out_vec);
+
+    // ---- once per CTA: tile-independent tables ------------------------------------------------
+    for (int t = tid; t < nT; t += NT) {
+        const uint32_t zl = a.t_zl[t];
+        const uint32_t zreg = (zl >> 5) & (R - 1);
+        uint32_t pat = 0;  // bit r = parity(zreg & r): sign pattern over the thread's R rows
+#pragma unroll
+        for (int r = 0; r < R; ++r) pat |= (uint32_t)(__popc(zreg & r) & 1) << r;
+        s_zp[t] = (zl & ~((uint32_t)(R - 1) << 5)) | (pat << 16);
+    }
+    for (int g = tid; g < nG; g += NT) s_hdr[g] = a.g_hdr[g];
+    for (int i = tid; i < 128; i += NT) s_spread[i] = a.spread[i];
+    if (MODE == MODE_BATCH)
+        for (int i = tid; i < NW * nG; i += NT) s_acc[i] = make_double2(0.0, 0.0);
+
+    const int low = a.low_bits;
+    const uint32_t lowmask = (1u << low) - 1u;
+    const int rows = 1 << (k - 5 - RB);
+    double e_re = 0.0, e_im = 0.0;
+
+    for (unsigned long long tile_id = blockIdx.x; tile_id < a.n_tiles; tile_id += gridDim.x) {
+        // shard position of the tile: deposit the tile number into the bits outside the tile mask
+        uint64_t base = 0;
+        {
+            unsigned long long rest = tile_id;
+            for (int r = 0; r < a.n_runs; ++r) {
+                const int len = a.run_len[r];
+                base |= (rest & ((1ull << len) - 1ull)) << a.run_pos[r];
+                rest >>= len;
+            }
+        }
+        __syncthreads();  // previous tile fully consumed (also orders the one-time tables)
+        {
+            const uint64_t kbase = base ^ a.ket_xor;
+            // 2^k / NT amplitudes per thread, 4 independent 128-bit loads in flight per step
+            for (uint32_t i0 = tid; i0 < tile_amps; i0 += 4 * NT) {
+                cplx_t v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t idx = i0 + u * NT;
+                    if (idx < tile_amps) {
+                        const uint64_t g = kbase | (idx & lowmask) | s_spread[(idx >> low) & 63] | s_spread[64 + ((idx >> (low + 6)) & 63)];
+                        v[u] = ld_stream(ket + g);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t idx = i0 + u * NT;
+                    if (idx < tile_amps) tile[idx] = v[u];
+                }
+            }
+            // coefficients with the sign of the z bits outside the tile (constant over the tile)
+            for (int t = tid; t < nT; t += NT) {
+                const bool neg = __popcll(a.t_zo[t] & base) & 1;
+                const double cr = a.t_cre[t];
+                s_cre[t] = (real_t)(neg ? -cr : cr);
+                if (CPLX) {
+                    const double ci = a.t_cim[t];
+                    s_cim[t] = (real_t)(neg ? -ci : ci);
+                }
+            }
+        }
+        __syncthreads();
+
+        for (int u = warp; u < rows; u += NW) {
+            const uint32_t jrow = ((uint32_t)u << (5 + RB)) | (uint32_t)lane;
+            real_t acc_re[R], acc_im[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) acc_re[r] = acc_im[r] = (real_t)0;
+            cplx_t brav[R];
+            if (MODE == MODE_BATCH) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const uint32_t j = jrow | ((uint32_t)r << 5);
+                    if (a.same_tile)
+                        brav[r] = tile[j];
+                    else
+                        brav[r] = bra[base | (j & lowmask) | s_spread[(j >> low) & 63] | s_spread[64 + ((j >> (low + 6)) & 63)]];
+                }
+            }
+            int tb = 0;
+            for (int g = 0; g < nG; ++g) {
+                const uint32_t hdr = s_hdr[g];
+                const uint32_t xl = hdr & 0xffffu;
+                const int nt = (int)((hdr >> 16) & 0x7fffu);
+                const bool imag = hdr >> 31;
+                real_t W[R], Wi[R];  // W_x(row) = sum_t c_t (-1)^{|z_t & row|}
+#pragma unroll
+                for (int r = 0; r < R; ++r) W[r] = Wi[r] = (real_t)0;
+                for (int t = tb; t < tb + nt; ++t) {
+                    const real_t c = s_cre[t];
+                    const uint32_t zp = s_zp[t];
+                    // sign bit of row r: parity of z over (lane, row) bits XOR the register pattern
+                    const uint32_t m = (zp >> 16) ^ (0u - (uint32_t)(__popc(zp & jrow) & 1));
+#pragma unroll
+                    for (int r = 0; r < R; ++r) add_signed(W[r], c, (m >> r) & 1u);
+                    if (CPLX) {
+                        const real_t ci = s_cim[t];
+#pragma unroll
+                        for (int r = 0; r < R; ++r) add_signed(Wi[r], ci, (m >> r) & 1u);
+                    }
+                }
+                tb += nt;
+                const uint32_t pj = jrow ^ xl;
+                double v_re = 0.0, v_im = 0.0;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const cplx_t p = tile[pj ^ ((uint32_t)r << 5)];
+                    const real_t w = W[r];
+                    real_t t_re, t_im;
+                    if (CPLX) {
+                        const real_t wi = Wi[r];
+                        t_re = w * p.x - wi * p.y;
+                        t_im = w * p.y + wi * p.x;
+                    } else if (imag) {
+                        t_re = -w * p.y;
+                        t_im = w * p.x;
+                    } else {
+                        t_re = w * p.x;
+                        t_im = w * p.y;
+                    }
+                    if (MODE == MODE_BATCH) {
+                        v_re += (double)brav[r].x * t_re + (double)brav[r].y * t_im;
+                        v_im += (double)brav[r].x * t_im - (double)brav[r].y * t_re;
+                    } else {
+                        acc_re[r] += t_re;
+                        acc_im[r] += t_im;
+                    }
+                }
+                if (MODE == MODE_BATCH) {
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) {
+                        v_re += __shfl_down_sync(0xffffffffu, v_re, d);
+                        v_im += __shfl_down_sync(0xffffffffu, v_im, d);
+                    }
+                    if (lane == 0) {  // only this warp writes its own row of s_acc: deterministic
+                        double2 cur = s_acc[warp * nG + g];
+                        cur.x += v_re;
+                        cur.y += v_im;
+                        s_acc[warp * nG + g] = cur;
+                    }
+                }
+            }
+            if (MODE != MODE_BATCH) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const uint32_t j = jrow | ((uint32_t)r << 5);
+                    const uint64_t gidx = base | (j & lowmask) | s_spread[(j >> low) & 63] | s_spread[64 + ((j >> (low + 6)) & 63)];
+                    if (MODE == MODE_EXPECT) {
+                        const cplx_t b = a.same_tile ? tile[j] : bra[gidx];
+                        e_re += (double)b.x * (double)acc_re[r] + (double)b.y * (double)acc_im[r];
+                        e_im += (double)b.x * (double)acc_im[r] - (double)b.y * (double)acc_re[r];
+                    } else {
+                        cplx_t y;
+                        if (a.accumulate) {
+                            y = yout[gidx];
+                            y.x += acc_re[r];
+                            y.y += acc_im[r];
+                        } else {
+                            y.x = acc_re[r];
+                            y.y = acc_im[r];
+                        }
+                        yout[gidx] = y;
+                    }
+                }
+            }
+        }
+    }
+
+    if (MODE == MODE_EXPECT) {
+        double2 tot = block_reduce_sum(make_double2(e_re, e_im), s_red);
+        if (tid == 0) a.partials[blockIdx.x] = tot;
+    } else if (MODE == MODE_BATCH) {
+        __syncthreads();
+        for (int g = tid; g < nG; g += NT) {
+            double2 s = make_double2(0.0, 0.0);
+            for (int w = 0; w < NW; ++w) {
+                s.x += s_acc[w * nG + g].x;
+                s.y += s_acc[w * nG + g].y;
+            }
+            a.partials[(size_t)g * gridDim.x + blockIdx.x] = s;
+        }
+    }
+}
+
+// ---- direct kernel: one thread per row, partners straight from global memory ------------------
+// Used for shards smaller than a tile (n_local < 8) and as an independent cross-check of the tile
+// kernel in the tests (QFE_FORCE_DIRECT=1).
+struct DirectArgs {
+    const void* ket;
+    const void* bra;
+    void* out_vec;
+    double2* partials;
+    const uint64_t* x;
+    const uint64_t* z;
+    const double* cre;
+    const double* cim;
+    const int64_t* range_begin;  // BATCH: per-group term ranges (device), indexed from range0
+    int64_t tb, te;              // EXPECT / APPLY: the class's term range
+    int range0;
+    int n_local;
+    int accumulate;
+};
+
+template <typename real_t, int MODE>
+__global__ void __launch_bounds__(256) direct_kernel(const DirectArgs a) {
+    using cplx_t = typename CplxOf<real_t>::type;
+    __shared__ double2 s_red[8];
+    const cplx_t* __restrict__ ket = reinterpret_cast<const cplx_t*>(a.ket);
+    const cplx_t* __restrict__ bra = reinterpret_cast<const cplx_t*>(a.bra);
+    cplx_t* __restrict__ yout = reinterpret_cast<cplx_t*>(a.out_vec);
+    int64_t tb = a.tb, te = a.te;
+    if (MODE == MODE_BATCH) {
+        tb = a.range_begin[a.range0 + blockIdx.y];
+        te = a.range_begin[a.range0 + blockIdx.y + 1];
+    }
+    const uint64_t n_amps = 1ull << a.n_local;
+    double e_re = 0.0, e_im = 0.0;
+    for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n_amps; b += (uint64_t)gridDim.x * blockDim.x) {
+        double acc_re = 0.0, acc_im = 0.0;
+        for (int64_t t = tb; t < te; ++t) {
+            const cplx_t p = ket[b ^ a.x[t]];
+            double cr = a.cre[t], ci = a.cim[t];
+            if (__popcll(a.z[t] & b) & 1) {
+                cr = -cr;
+                ci = -ci;
+            }
+            acc_re += cr * (double)p.x - ci * (double)p.y;
+            acc_im += cr * (double)p.y + ci * (double)p.x;
+        }
+        if (MODE == MODE_APPLY) {
+            cplx_t y;
+            if (a.accumulate) {
+                y = yout[b];
+                y.x += (real_t)acc_re;
+                y.y += (real_t)acc_im;
+            } else {
+                y.x = (real_t)acc_re;
+                y.y = (real_t)acc_im;
+            }
+            yout[b] = y;
+        } else {
+            const cplx_t v = bra[b];
+            e_re += (double)v.x * acc_re + (double)v.y * acc_im;
+            e_im += (double)v.x * acc_im - (double)v.y * acc_re;
+        }
+    }
+    if (MODE != MODE_APPLY) {
+        double2 tot = block_reduce_sum(make_double2(e_re, e_im), s_red);
+        if (threadIdx.x == 0) a.partials[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = tot;
+    }
+}
+
+// vals[r] = sum_b partials[r * n_blocks + b], one warp per range, fixed order
+__global__ void __launch_bounds__(128) reduce_partials(const double2* __restrict__ partials, int n_ranges, int n_blocks, double2* __restrict__ vals) {
+    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= n_ranges) return;
+    double sx = 0.0, sy = 0.0;
+    for (int b = lane; b < n_blocks; b += 32) {
+        const double2 p = partials[(size_t)r * n_blocks + b];
+        sx += p.x;
+        sy += p.y;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        sx += __shfl_down_sync(0xffffffffu, sx, d);
+        sy += __shfl_down_sync(0xffffffffu, sy, d);
+    }
+    if (lane == 0) vals[r] = make_double2(sx, sy);
+}
+
+int reduce_to_vals(qfe_ctx* ctx, const double2* partials, int n_ranges, int n_blocks, double2* vals) {
+    reduce_partials<<<(n_ranges + 3) / 4, 128, 0, ctx->stream>>>(partials, n_ranges, n_blocks, vals);
+    ctx->launches++;
+    QFE_CUDA(cudaGetLastError());
+    return QFE_OK;
+}
+
+}  // namespace qfe
+
+using namespace qfe;
+
+struct qfe_plan {
+    PlanHost h;
+    PlanLimits lim;
+    bool batch = false;
+    bool force_direct = false;
+    int device = 0;
+    DevBuf g_hdr, t_zl, t_zo, t_cre, t_cim, d_x, d_z, d_cre, d_cim, dg_begin;
+};
+
+namespace qfe {
+
+template <typename T>
+static int upload(DevBuf& buf, const std::vector<T>& v, cudaStream_t s) {
+    QFE_TRY(buf.alloc(sizeof(T) * (v.empty() ? 1 : v.size())));
+    if (!v.empty()) QFE_CUDA(cudaMemcpyAsync(buf.p, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice, s));
+    return QFE_OK;
+}
+
+static int find_class(const qfe_plan* p, int x_hi) {
+    for (size_t i = 0; i < p->h.classes.size(); ++i)
+        if (p->h.classes[i].x_hi == x_hi) return (int)i;
+    return -1;
+}
+
+template <typename real_t, bool CPLX, int MODE>
+static int launch_tile(qfe_ctx* ctx, const SweepArgs& args, int grid, size_t smem) {
+    auto kern = tile_sweep_kernel<real_t, RBITS, CPLX, MODE>;
+    if (smem > 48 * 1024) QFE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, NT, smem, ctx->stream>>>(args);
+    ctx->launches++;
+    QFE_CUDA(cudaGetLastError());
+    return QFE_OK;
+}
+
+template <typename real_t, int MODE>
+static int launch_tile_c(qfe_ctx* ctx, const SweepArgs& args, int grid, size_t smem, bool cplx) {
+    return cplx ? launch_tile<real_t, true, MODE>(ctx, args, grid, smem) : launch_tile<real_t, false, MODE>(ctx, args, grid, smem);
+}
+
+template <int MODE>
+static int launch_tile_d(qfe_ctx* ctx, const SweepArgs& args, int grid, size_t smem, bool cplx, int dtype) {
+    return dtype == QFE_C128 ? launch_tile_c<double, MODE>(ctx, args, grid, smem, cplx) : launch_tile_c<float, MODE>(ctx, args, grid, smem, cplx);
+}
+
+template <int MODE>
+static int launch_direct(qfe_ctx* ctx, const DirectArgs& args, dim3 grid, int dtype) {
+    if (dtype == QFE_C128)
+        direct_kernel<double, MODE><<<grid, 256, 0, ctx->stream>>>(args);
+    else
+        direct_kernel<float, MODE><<<grid, 256, 0, ctx->stream>>>(args);
+    ctx->launches++;
+    QFE_CUDA(cudaGetLastError());
+    return QFE_OK;
+}
+
+static void fill_sweep_args(const qfe_plan* p, const SweepHost& s, SweepArgs& a) {
+    a.g_hdr = p->g_hdr.as<uint32_t>() + s.group_begin;
+    a.t_zl = p->t_zl.as<uint32_t>() + s.term_begin;
+    a.t_zo = p->t_zo.as<uint64_t>() + s.term_begin;
+    a.t_cre = p->t_cre.as<double>() + s.term_begin;
+    a.t_cim = p->t_cim.as<double>() + s.term_begin;
+    a.n_groups = s.group_end - s.group_begin;
+    a.n_terms = (int)(s.term_end - s.term_begin);
+    a.k = s.k;
+    a.low_bits = s.low_bits;
+    a.n_runs = s.n_runs;
+    a.n_tiles = (unsigned long long)s.n_tiles;
+    a.ket_xor = s.ket_xor;
+    memcpy(a.run_pos, s.run_pos, sizeof(a.run_pos));
+    memcpy(a.run_len, s.run_len, sizeof(a.run_len));
+    memcpy(a.spread, s.spread[0], 64 * sizeof(uint64_t));
+    memcpy(a.spread + 64, s.spread[1], 64 * sizeof(uint64_t));
+}
+
+// Runs every sweep of one class in EXPECT or BATCH mode and leaves per-range values in host_vals
+// (EXPECT: one value per sweep; BATCH: one per group, sweep order).
+static int run_class_reduce(qfe_ctx* ctx, const qfe_plan* p, int ci, const void* bra, const void* ket, int dtype, std::vector<double>& host_vals,
+                            std::vector<int32_t>& val_slot) {
+    const ClassHost& cls = p->h.classes[ci];
+    const bool batch = p->batch;
+    const bool tiles = p->h.use_tiles && !p->force_direct;
+    cudaStream_t s = ctx->stream;
+    host_vals.clear();
+    val_slot.clear();
+    int64_t n_vals = 0;
+    if (tiles) {
+        for (int si = cls.sweep_begin; si < cls.sweep_end; ++si) n_vals += batch ? (p->h.sweeps[si].group_end - p->h.sweeps[si].group_begin) : 1;
+    } else {
+        n_vals = batch ? (cls.dgroup_end - cls.dgroup_begin) : 1;
+    }
+    if (n_vals == 0) return QFE_OK;
+    QFE_TRY(ctx->result.reserve(sizeof(double2) * n_vals));
+    double2* d_vals = ctx->result.as<double2>();
+    int64_t vpos = 0;
+    if (tiles) {
+        size_t max_partials = 1;
+        for (int si = cls.sweep_begin; si < cls.sweep_end; ++si) {
+            const SweepHost& sw = p->h.sweeps[si];
+            const size_t grid = (size_t)std::min<int64_t>(sw.n_tiles, ctx->sm_count);
+            max_partials = std::max(max_partials, grid * (size_t)(batch ? sw.group_end - sw.group_begin : 1));
+        }
+        QFE_TRY(ctx->partials.reserve(sizeof(double2) * max_partials));
+        for (int si = cls.sweep_begin; si < cls.sweep_end; ++si) {
+            const SweepHost& sw = p->h.sweeps[si];
+            SweepArgs a;
+            memset(&a, 0, sizeof(a));
+            fill_sweep_args(p, sw, a);
+            a.ket = ket;
+            a.bra = bra;
+            a.same_tile = (bra == ket && sw.ket_xor == 0) ? 1 : 0;
+            const int grid = (int)std::min<int64_t>(sw.n_tiles, ctx->sm_count);
+            const int n_ranges = batch ? a.n_groups : 1;
+            a.partials = ctx->partials.as<double2>();
+            const size_t real_bytes = dtype == QFE_C128 ? 8 : 4;
+            const SmemLayout L = smem_layout(sw.k, a.n_terms, a.n_groups, real_bytes, sw.complex_w, batch);
+            if (batch)
+                QFE_TRY(launch_tile_d<MODE_BATCH>(ctx, a, grid, L.total, sw.complex_w, dtype));
+            else
+                QFE_TRY(launch_tile_d<MODE_EXPECT>(ctx, a, grid, L.total, sw.complex_w, dtype));
+            reduce_partials<<<(n_ranges + 3) / 4, 128, 0, s>>>(a.partials, n_ranges, grid, d_vals + vpos);
+            ctx->launches++;
+            QFE_CUDA(cudaGetLastError());
+            for (int g = 0; g < n_ranges; ++g) val_slot.push_back(batch ? p->h.g_slot[sw.group_begin + g] : 0);
+            vpos += n_ranges;
+        }
+    } else {
+        DirectArgs a;
+        memset(&a, 0, sizeof(a));
+        a.ket = ket;
+        a.bra = bra;
+        a.x = p->d_x.as<uint64_t>();
+        a.z = p->d_z.as<uint64_t>();
+        a.cre = p->d_cre.as<double>();
+        a.cim = p->d_cim.as<double>();
+        a.range_begin = p->dg_begin.as<int64_t>();
+        a.range0 = cls.dgroup_begin;
+        a.tb = cls.dterm_begin;
+        a.te = cls.dterm_end;
+        a.n_local = p->h.n_local;
+        const int64_t n_amps = int64_t(1) << p->h.n_local;
+        const int gx = (int)std::min<int64_t>((n_amps + 255) / 256, (int64_t)ctx->sm_count * 4);
+        const int n_ranges = (int)n_vals;
+        QFE_TRY(ctx->partials.reserve(sizeof(double2) * (size_t)n_ranges * gx));
+        a.partials = ctx->partials.as<double2>();
+        // gridDim.y is limited to 65535 ranges per launch
+        for (int r0 = 0; r0 < n_ranges; r0 += 32768) {
+            const int nr = std::min(32768, n_ranges - r0);
+            DirectArgs b = a;
+            b.range0 = cls.dgroup_begin + r0;
+            b.partials = a.partials + (size_t)r0 * gx;
+            if (batch)
+                QFE_TRY(launch_direct<MODE_BATCH>(ctx, b, dim3(gx, nr), dtype));
+            else
+                QFE_TRY(launch_direct<MODE_EXPECT>(ctx, b, dim3(gx, 1), dtype));
+        }
+        reduce_partials<<<(n_ranges + 3) / 4, 128, 0, s>>>(a.partials, n_ranges, gx, d_vals);
+        ctx->launches++;
+        QFE_CUDA(cudaGetLastError());
+        for (int g = 0; g < n_ranges; ++g) val_slot.push_back(batch ? p->h.dg_slot[cls.dgroup_begin + g] : 0);
+        vpos = n_ranges;
+    }
+    host_vals.resize(2 * n_vals);
+    QFE_CUDA(cudaMemcpyAsync(host_vals.data(), d_vals, sizeof(double2) * n_vals, cudaMemcpyDeviceToHost, s));
+    QFE_CUDA(cudaStreamSynchronize(s));
+    return QFE_OK;
+}
+
+}  // namespace qfe
+
+extern "C" {
+
+int qfe_plan_create(qfe_ctx* ctx, const qfe_terms* t, int n_local, int shard, int tile_bits, qfe_plan** out) {
+    QFE_REQUIRE(ctx && t && out, QFE_ERR_ARG, "qfe_plan_create: null argument");
+    QFE_REQUIRE(n_local >= 0 && n_local <= t->n, QFE_ERR_ARG, "qfe_plan_create: n_local=%d outside 0..%d", n_local, t->n);
+    QFE_REQUIRE(n_local <= 40, QFE_ERR_UNSUPPORTED, "qfe_plan_create: shards above 2^40 amplitudes are not supported");
+    QFE_CUDA(cudaSetDevice(ctx->device));
+    qfe_plan* p = new (std::nothrow) qfe_plan();
+    QFE_REQUIRE(p, QFE_ERR_OOM, "out of host memory");
+    p->device = ctx->device;
+    p->batch = t->n_slots > 1;
+    const char* fd = getenv("QFE_FORCE_DIRECT");
+    p->force_direct = (tile_bits < 0) || (fd && fd[0] == '1');
+    PlanLimits lim;
+    lim.tile_bits = tile_bits > 0 ? tile_bits : 13;
+    if (lim.tile_bits > 13) lim.tile_bits = 13;  // 2^13 complex128 amplitudes = 128 KB of the 227 KB shared memory
+    if (p->batch) {
+        lim.max_terms = 1024;
+        lim.max_groups = 128;
+    } else {
+        lim.max_terms = 4096;
+        lim.max_groups = 1024;
+    }
+    p->lim = lim;
+    TermView v;
+    v.n = t->n;
+    v.T = t->T;
+    v.x = t->x.data();
+    v.z = t->z.data();
+    v.c = t->c.data();
+    v.owner = t->owner.data();
+    v.n_slots = t->n_slots;
+    v.constant = t->constant.data();
+    const char* err = nullptr;
+    if (build_plan(v, n_local, shard, lim, p->h, &err) != 0) {
+        set_error("%s", err ? err : "build_plan failed");
+        delete p;
+        return QFE_ERR_ARG;
+    }
+    cudaStream_t s = ctx->stream;
+    int rc = QFE_OK;
+    if ((rc = upload(p->g_hdr, p->h.g_hdr, s)) || (rc = upload(p->t_zl, p->h.t_zl, s)) || (rc = upload(p->t_zo, p->h.t_zo, s)) ||
+        (rc = upload(p->t_cre, p->h.t_cre, s)) || (rc = upload(p->t_cim, p->h.t_cim, s)) || (rc = upload(p->d_x, p->h.d_x, s)) ||
+        (rc = upload(p->d_z, p->h.d_z, s)) || (rc = upload(p->d_cre, p->h.d_cre, s)) || (rc = upload(p->d_cim, p->h.d_cim, s)) ||
+        (rc = upload(p->dg_begin, p->h.dg_begin, s))) {
+        delete p;
+        return rc;
+    }
+    QFE_CUDA(cudaStreamSynchronize(s));
+    *out = p;
+    return QFE_OK;
+}
+
+int qfe_plan_info(const qfe_plan* p, int64_t* n_sweeps, int64_t* n_groups, int64_t* n_terms, int32_t* n_classes, int32_t* tile_bits) {
+    QFE_REQUIRE(p, QFE_ERR_ARG, "null plan");
+    const bool tiles = p->h.use_tiles && !p->force_direct;
+    if (n_sweeps) *n_sweeps = tiles ? (int64_t)p->h.sweeps.size() : (int64_t)p->h.classes.size();
+    if (n_groups) *n_groups = (int64_t)p->h.dg_slot.size();
+    if (n_terms) *n_terms = (int64_t)p->h.d_x.size();
+    if (n_classes) *n_classes = (int32_t)p->h.classes.size();
+    if (tile_bits) *tile_bits = tiles ? p->h.k : 0;
+    return QFE_OK;
+}
+
+int qfe_plan_geometry(const qfe_plan* p, int* nqbits, int* n_local) {
+    QFE_REQUIRE(p, QFE_ERR_ARG, "null plan");
+    if (nqbits) *nqbits = p->h.n;
+    if (n_local) *n_local = p->h.n_local;
+    return QFE_OK;
+}
+
+int qfe_plan_classes(const qfe_plan* p, int32_t* x_hi, int32_t capacity) {
+    QFE_REQUIRE(p && x_hi, QFE_ERR_ARG, "null argument");
+    QFE_REQUIRE(capacity >= (int32_t)p->h.classes.size(), QFE_ERR_ARG, "qfe_plan_classes: capacity %d < %zu classes", capacity, p->h.classes.size());
+    for (size_t i = 0; i < p->h.classes.size(); ++i) x_hi[i] = p->h.classes[i].x_hi;
+    return QFE_OK;
+}
+
+int qfe_plan_destroy(qfe_plan* p) {
+    if (p) cudaSetDevice(p->device);
+    delete p;
+    return QFE_OK;
+}
+
+int qfe_expectation_class(qfe_ctx* ctx, const qfe_plan* p, int x_hi, const void* bra, const void* ket, int dtype, double* out) {
+    QFE_REQUIRE(ctx && p && bra && ket && out, QFE_ERR_ARG, "qfe_expectation_class: null argument");
+    QFE_REQUIRE(dtype == QFE_C128 || dtype == QFE_C64, QFE_ERR_ARG, "unknown dtype %d", dtype);
+    QFE_CUDA(cudaSetDevice(ctx->device));
+    for (int64_t i = 0; i < 2 * p->h.n_slots; ++i) out[i] = 0.0;
+    const int ci = find_class(p, x_hi);
+    if (ci < 0) return QFE_OK;  // no term flips these high qubits
+    std::vector<double> vals;
+    std::vector<int32_t> slots;
+    QFE_TRY(run_class_reduce(ctx, p, ci, bra, ket, dtype, vals, slots));
+    for (size_t i = 0; i < slots.size(); ++i) {
+        out[2 * slots[i]] += vals[2 * i];
+        out[2 * slots[i] + 1] += vals[2 * i + 1];
+    }
+    return QFE_OK;
+}
+
+int qfe_expectation(qfe_ctx* ctx, const qfe_plan* p, const void* psi, int dtype, double out[2]) {
+    QFE_REQUIRE(ctx && p && psi && out, QFE_ERR_ARG, "qfe_expectation: null argument");
+    QFE_REQUIRE(p->h.n_local == p->h.n, QFE_ERR_STATE, "qfe_expectation needs an unsharded plan (n_local == nqbits); use qfe_expectation_class");
+    QFE_REQUIRE(p->h.n_slots == 1, QFE_ERR_STATE, "qfe_expectation needs a single-operator term set");
+    return qfe_expectation_class(ctx, p, 0, psi, psi, dtype, out);
+}
+
+int qfe_expectation_host(qfe_ctx* ctx, const qfe_plan* p, const void* psi_host, int dtype, double out[2]) {
+    QFE_REQUIRE(ctx && p && psi_host && out, QFE_ERR_ARG, "qfe_expectation_host: null argument");
+    QFE_REQUIRE(p->h.n_local == p->h.n, QFE_ERR_STATE, "qfe_expectation_host needs an unsharded plan");
+    QFE_CUDA(cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t(1) << p->h.n) * (dtype == QFE_C128 ? 16 : 8);
+    QFE_TRY(ctx->hostvec.reserve(bytes));
+    // chunked upload: many modest copies instead of one huge one (the source may be pageable)
+    const size_t chunk = size_t(1) << 28;
+    for (size_t off = 0; off < bytes; off += chunk) {
+        const size_t nb = std::min(chunk, bytes - off);
+        QFE_CUDA(cudaMemcpyAsync(ctx->hostvec.as<char>() + off, (const char*)psi_host + off, nb, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return qfe_expectation(ctx, p, ctx->hostvec.p, dtype, out);
+}
+
+int qfe_apply_class(qfe_ctx* ctx, const qfe_plan* p, int x_hi, const void* ket, void* y, int dtype, int accumulate) {
+    QFE_REQUIRE(ctx && p && ket && y, QFE_ERR_ARG, "qfe_apply_class: null argument");
+    QFE_REQUIRE(dtype == QFE_C128 || dtype == QFE_C64, QFE_ERR_ARG, "unknown dtype %d", dtype);
+    QFE_REQUIRE(p->h.n_slots == 1, QFE_ERR_STATE, "qfe_apply_class needs a single-operator term set");
+    QFE_REQUIRE(ket != y, QFE_ERR_ARG, "qfe_apply_class: in-place apply is not supported");
+    QFE_CUDA(cudaSetDevice(ctx->device));
+    const int ci = find_class(p, x_hi);
+    const size_t bytes = (size_t(1) << p->h.n_local) * (dtype == QFE_C128 ? 16 : 8);
+    if (ci < 0) {
+        if (!accumulate) QFE_CUDA(cudaMemsetAsync(y, 0, bytes, ctx->stream));
+        return QFE_OK;
+    }
+    const ClassHost& cls = p->h.classes[ci];
+    const bool tiles = p->h.use_tiles && !p->force_direct;
+    if (tiles) {
+        if (cls.sweep_begin == cls.sweep_end && !accumulate) QFE_CUDA(cudaMemsetAsync(y, 0, bytes, ctx->stream));
+        for (int si = cls.sweep_begin; si < cls.sweep_end; ++si) {
+            const SweepHost& sw = p->h.sweeps[si];
+            SweepArgs a;
+            memset(&a, 0, sizeof(a));
+            fill_sweep_args(p, sw, a);
+            a.ket = ket;
+            a.bra = ket;
+            a.out_vec = y;
+            a.same_tile = 0;
+            a.accumulate = (si == cls.sweep_begin) ? (accumulate ? 1 : 0) : 1;
+            const int grid = (int)std::min<int64_t>(sw.n_tiles, ctx->sm_count);
+            const SmemLayout L = smem_layout(sw.k, a.n_terms, a.n_groups, dtype == QFE_C128 ? 8 : 4, sw.complex_w, false);
+            QFE_TRY(launch_tile_d<MODE_APPLY>(ctx, a, grid, L.total, sw.complex_w, dtype));
+        }
+    } else {
+        DirectArgs a;
+        memset(&a, 0, sizeof(a));
+        a.ket = ket;
+        a.bra = ket;
+        a.out_vec = y;
+        a.x = p->d_x.as<uint64_t>();
+        a.z = p->d_z.as<uint64_t>();
+        a.cre = p->d_cre.as<double>();
+        a.cim = p->d_cim.as<double>();
+        a.tb = cls.dterm_begin;
+        a.te = cls.dterm_end;
+        a.n_local = p->h.n_local;
+        a.accumulate = accumulate ? 1 : 0;
+        const int64_t n_amps = int64_t(1) << p->h.n_local;
+        const int gx = (int)std::min<int64_t>((n_amps + 255) / 256, (int64_t)ctx->sm_count * 4);
+        QFE_TRY(launch_direct<MODE_APPLY>(ctx, a, dim3(gx, 1), dtype));
+    }
+    return QFE_OK;
+}
+
+int qfe_apply(qfe_ctx* ctx, const qfe_plan* p, const void* psi, void* y, int dtype) {
+    QFE_REQUIRE(ctx && p && psi && y, QFE_ERR_ARG, "qfe_apply: null argument");
+    QFE_REQUIRE(p->h.n_local == p->h.n, QFE_ERR_STATE, "qfe_apply needs an unsharded plan (n_local == nqbits); use qfe_apply_class");
+    return qfe_apply_class(ctx, p, 0, psi, y, dtype, 0);
+}
+
+int qfe_commutator_gradients(qfe_ctx* ctx, const qfe_plan* h_plan, const qfe_plan* pool_plan, const void* psi, void* scratch, int dtype,
+                             double* grads) {
+    QFE_REQUIRE(ctx && h_plan && pool_plan && psi && scratch && grads, QFE_ERR_ARG, "qfe_commutator_gradients: null argument");
+    QFE_REQUIRE(h_plan->h.n_local == h_plan->h.n && pool_plan->h.n_local == pool_plan->h.n && h_plan->h.n == pool_plan->h.n, QFE_ERR_STATE,
+                "qfe_commutator_gradients needs unsharded plans on the same register");
+    // phi = H psi, then g_k = 2 Im <phi| tau_k |psi>
+    QFE_TRY(qfe_apply(ctx, h_plan, psi, scratch, dtype));
+    std::vector<double> vals(2 * pool_plan->h.n_slots);
+    QFE_TRY(qfe_expectation_class(ctx, pool_plan, 0, scratch, psi, dtype, vals.data()));
+    for (int64_t k = 0; k < pool_plan->h.n_slots; ++k) grads[k] = 2.0 * vals[2 * k + 1];
+    return QFE_OK;
+}
+
+}  // extern "C"
