@@ -245,6 +245,39 @@ class Engine:
         self.sync()
         return out
 
+    # ---- shard-level entry points (one x_hi class at a time; ShardedEngine drives these) ------
+    def expectation_class(self, plan: Plan, x_hi: int, bra_shard, ket_shard):
+        """Class x_hi's share of <bra|H|ket>: ``bra_shard`` is this rank's shard of the bra,
+        ``ket_shard`` the shard (shard ^ x_hi) of the ket."""
+        n_amps = 1 << plan.n_local
+        dt = self._check_state(ket_shard, n_amps)
+        if self._check_state(bra_shard, n_amps) != dt:
+            raise TypeError("bra and ket dtypes differ")
+        self._sync_torch()
+        out = np.zeros(2 * plan.terms.n_slots, dtype=np.float64)
+        check(
+            self.lib.qfe_expectation_class(
+                self.ctx, plan.handle, x_hi, C.c_void_p(bra_shard.data_ptr()), C.c_void_p(ket_shard.data_ptr()), dt, as_ptr(out, C.c_double)
+            )
+        )
+        vals = out.view(np.complex128)
+        return complex(vals[0]) if plan.terms.n_slots == 1 else vals.copy()
+
+    def apply_class(self, plan: Plan, x_hi: int, ket_shard, y_shard, accumulate: bool, sync: bool = True) -> None:
+        """y_shard (+)= H_class(x_hi) ket_shard, where ket_shard is the shard (shard ^ x_hi) of the ket."""
+        n_amps = 1 << plan.n_local
+        dt = self._check_state(ket_shard, n_amps)
+        if self._check_state(y_shard, n_amps) != dt:
+            raise TypeError("ket and output dtypes differ")
+        self._sync_torch()
+        check(
+            self.lib.qfe_apply_class(
+                self.ctx, plan.handle, x_hi, C.c_void_p(ket_shard.data_ptr()), C.c_void_p(y_shard.data_ptr()), dt, 1 if accumulate else 0
+            )
+        )
+        if sync:
+            self.sync()
+
     def commutator_gradients(self, h_plan, pool_plan, psi, scratch=None) -> np.ndarray:
         """g_k = -i <psi|[H, tau_k]|psi> for every pool operator (adapt_vqe.py:181-185)."""
         torch = _torch()

@@ -1,0 +1,145 @@
+"""CPU check of the sweep planner (host C++ of kernel 2): the plan it emits -- tile masks covering
+every X mask, tile geometry, compressed z masks, folded coefficients -- is interpreted by a scalar
+CPU walker (tests/csrc/plan_emul.cpp) and compared with the oracle's matrix-free formula.
+No GPU involved; the CUDA kernel consumes exactly the same plan arrays."""
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import models, spin, transforms
+
+HERE = Path(__file__).resolve().parent
+LIB = HERE / "csrc" / "libplan_emul.so"
+
+
+@pytest.fixture(scope="module")
+def emul():
+    subprocess.run(["make", "-C", str(HERE / "csrc")], check=True, capture_output=True)
+    lib = C.CDLL(str(LIB))
+    P = C.POINTER
+    lib.plan_emul_run.restype = C.c_int
+    lib.plan_emul_run.argtypes = [
+        C.c_int, C.c_int64, P(C.c_uint64), P(C.c_uint64), P(C.c_double), P(C.c_int32), C.c_int64, P(C.c_double),
+        C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, P(C.c_double), P(C.c_double), P(C.c_double), P(C.c_double), P(C.c_int64),
+    ]
+    return lib
+
+
+def _run(lib, n, x, z, c, owner, n_slots, constant, n_local, shard, tile_bits, x_hi, bra, ket, max_terms=4096, max_groups=1024):
+    x = np.ascontiguousarray(x, dtype=np.uint64)
+    z = np.ascontiguousarray(z, dtype=np.uint64)
+    c = np.ascontiguousarray(c, dtype=np.complex128)
+    owner = np.ascontiguousarray(owner, dtype=np.int32)
+    constant = np.ascontiguousarray(constant, dtype=np.complex128)
+    out = np.zeros(n_slots, dtype=np.complex128)
+    y = np.zeros(1 << n_local, dtype=np.complex128)
+    stats = np.zeros(4, dtype=np.int64)
+    ptr = lambda a, t: a.view(np.float64).ctypes.data_as(C.POINTER(t)) if a.dtype == np.complex128 else a.ctypes.data_as(C.POINTER(t))
+    rc = lib.plan_emul_run(
+        n, len(x), ptr(x, C.c_uint64), ptr(z, C.c_uint64), ptr(c, C.c_double), ptr(owner, C.c_int32), n_slots, ptr(constant, C.c_double),
+        n_local, shard, tile_bits, max_terms, max_groups, x_hi, ptr(np.ascontiguousarray(bra), C.c_double), ptr(np.ascontiguousarray(ket), C.c_double),
+        ptr(out, C.c_double), ptr(y, C.c_double), ptr(stats, C.c_int64),
+    )
+    assert rc == 0, f"plan_emul_run failed with code {rc}"
+    return out, y, stats
+
+
+def _state(n, seed):
+    rng = np.random.default_rng(seed)
+    v = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)
+    return v / np.linalg.norm(v)
+
+
+def _molecule(m, enc, constant=0.0):
+    one, two = models.synthetic_integrals(m, seed=1234)
+    hpq, hpqrs = models.convert_to_h_integrals(one, two)
+    return transforms.transform(2 * m, models.electronic_terms(hpq, hpqrs), constant, enc).canonical()
+
+
+@pytest.mark.parametrize("enc", ["jordan-wigner", "bravyi-kitaev", "parity"])
+@pytest.mark.parametrize("tile_bits", [8, 10, 12])
+def test_unsharded_plan_reproduces_apply_and_expectation(emul, enc, tile_bits):
+    n = 12
+    x, z, c, k = _molecule(6, enc, constant=0.4)
+    psi, bra = _state(n, 0), _state(n, 1)
+    want_phi = spin.apply_packed(n, x, z, c, k, psi)
+    out, y, stats = _run(emul, n, x, z, c, np.zeros(len(x)), 1, [k], n, 0, tile_bits, 0, bra, psi)
+    assert np.max(np.abs(y - want_phi)) <= 1e-12 * np.max(np.abs(want_phi))
+    assert abs(out[0] - np.vdot(bra, want_phi)) <= 1e-12
+    n_groups = len(set(x.tolist())) + (0 if 0 in set(x.tolist()) else 1)  # + identity group if no diagonal term
+    assert stats[1] == n_groups and stats[2] == len(x) + 1
+    assert 1 <= stats[0] <= n_groups
+
+
+@pytest.mark.parametrize("n_local", [8, 10])
+def test_sharded_classes_recombine(emul, n_local):
+    n = 12
+    x, z, c, k = _molecule(6, "bravyi-kitaev", constant=-0.3)
+    psi = _state(n, 2)
+    want_phi = spin.apply_packed(n, x, z, c, k, psi)
+    want_e = np.vdot(psi, want_phi)
+    g = n - n_local
+    phi = np.zeros_like(psi)
+    total = 0.0
+    for r in range(1 << g):
+        for x_hi in range(1 << g):
+            own = psi[r << n_local : (r + 1) << n_local]
+            partner = psi[(r ^ x_hi) << n_local : ((r ^ x_hi) + 1) << n_local]
+            out, y, _ = _run(emul, n, x, z, c, np.zeros(len(x)), 1, [k], n_local, r, 8, x_hi, own, partner)
+            phi[r << n_local : (r + 1) << n_local] += y
+            total += out[0]
+    assert np.max(np.abs(phi - want_phi)) <= 1e-12 * np.max(np.abs(want_phi))
+    assert abs(total - want_e) <= 1e-12 * abs(want_e)
+
+
+def test_wide_masks_and_capacity_splits(emul):
+    """X masks wider than a tile (non-zero ket_xor sweeps), complex coefficients, groups larger
+    than the per-sweep staging capacity, several operator slots."""
+    n = 11
+    rng = np.random.default_rng(3)
+    T = 300
+    x = rng.integers(0, 1 << n, size=T, dtype=np.uint64)
+    x[:120] = x[0]  # one big group
+    z = rng.integers(0, 1 << n, size=T, dtype=np.uint64)
+    c = rng.standard_normal(T) + 1j * rng.standard_normal(T)
+    ps = spin.PauliSum(n)
+    owner = np.sort(rng.integers(0, 3, size=T)).astype(np.int32)
+    # canonical order inside every slot: ascending (x, z), no duplicates
+    recs = sorted({(int(o), int(a), int(b)) for o, a, b in zip(owner, x, z) if (a, b) != (0, 0)})
+    owner = np.array([r[0] for r in recs], dtype=np.int32)
+    x = np.array([r[1] for r in recs], dtype=np.uint64)
+    z = np.array([r[2] for r in recs], dtype=np.uint64)
+    c = c[: len(recs)]
+    consts = np.array([0.5, 0.0, -0.25j])
+    psi, bra = _state(n, 4), _state(n, 5)
+    out, y, stats = _run(emul, n, x, z, c, owner, 3, consts, n, 0, 8, 0, bra, psi, max_terms=64, max_groups=16)
+    want_total = np.zeros_like(psi)
+    for s in range(3):
+        sel = owner == s
+        phi = spin.apply_packed(n, x[sel], z[sel], c[sel], consts[s], psi)
+        assert abs(out[s] - np.vdot(bra, phi)) <= 1e-11, s
+        want_total += phi
+    assert np.max(np.abs(y - want_total)) <= 1e-11
+    assert stats[0] > 3  # capacity limits force several sweeps
+    del ps
+
+
+def test_uccsd_pool_batch(emul):
+    """Operator pool as one batched term set: every slot's <bra|tau_k|ket> (ADAPT gradient sweep)."""
+    n = 10
+    pool = [transforms.transform(n, op, 0.0, "jordan-wigner").canonical() for op in models.cluster_ops(4, n)]
+    x = np.concatenate([p[0] for p in pool])
+    z = np.concatenate([p[1] for p in pool])
+    c = np.concatenate([p[2] for p in pool])
+    owner = np.concatenate([np.full(len(p[0]), i) for i, p in enumerate(pool)])
+    K = len(pool)
+    psi, bra = _state(n, 6), _state(n, 7)
+    out, _, stats = _run(emul, n, x, z, c, owner, K, np.zeros(K), n, 0, 9, 0, bra, psi, max_terms=1024, max_groups=128)
+    for i, p in enumerate(pool):
+        want = np.vdot(bra, spin.apply_packed(n, p[0], p[1], p[2], 0.0, psi))
+        assert abs(out[i] - want) <= 1e-12, i
+    assert stats[1] == K
