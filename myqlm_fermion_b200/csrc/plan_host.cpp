@@ -108,7 +108,7 @@ int build_plan(const TermView& t, int n_local, int shard, const PlanLimits& lim,
         if (err) *err = e_arg;
         return 1;
     }
-    if (lim.tile_bits > PLAN_MAX_TILE_BITS || lim.max_terms > 32767 || lim.max_terms < 1 || lim.max_groups < 1) {
+    if (lim.tile_bits > PLAN_MAX_TILE_BITS || lim.max_terms > (int)HDR_NT_MASK || lim.max_terms < 1 || lim.max_groups < 1) {
         if (err) *err = "build_plan: limits out of range";
         return 1;
     }
@@ -125,19 +125,21 @@ int build_plan(const TermView& t, int n_local, int shard, const PlanLimits& lim,
         int32_t slot;
         uint64_t x, z;
         double re, im;
+        bool herm;  // Term.coeff is real: the term is Hermitian on its own
     };
     std::vector<TRec> recs;
     recs.reserve(t.T + t.n_slots);
     {
         int64_t i = 0;
         for (int64_t s = 0; s < t.n_slots; ++s) {
-            if (t.constant && (t.constant[2 * s] != 0.0 || t.constant[2 * s + 1] != 0.0)) recs.push_back({(int32_t)s, 0, 0, t.constant[2 * s], t.constant[2 * s + 1]});
+            if (t.constant && (t.constant[2 * s] != 0.0 || t.constant[2 * s + 1] != 0.0)) recs.push_back({(int32_t)s, 0, 0, t.constant[2 * s], t.constant[2 * s + 1], t.constant[2 * s + 1] == 0.0});
             while (i < t.T && (t.owner ? t.owner[i] : 0) == s) {
                 TRec r;
                 r.slot = (int32_t)s;
                 r.x = t.x[i];
                 r.z = t.z[i];
                 gather_coeff(t, i, n_local, shard, r.re, r.im);
+                r.herm = t.c[2 * i + 1] == 0.0;
                 recs.push_back(r);
                 ++i;
             }
@@ -282,25 +284,41 @@ int build_plan(const TermView& t, int n_local, int shard, const PlanLimits& lim,
                         cplx = true;
                 }
                 s.complex_w = cplx;
-                s.group_begin = (int32_t)out.g_hdr.size();
+                s.group_begin = (int32_t)(out.g_hdr.size() / 2);
                 s.term_begin = (int64_t)out.t_zl.size();
+                const uint32_t regmask = (1u << PLAN_REG_BITS) - 1u;
                 for (size_t a = 0; a < take.size(); ++a) {
                     const Group& g = groups[take[a]];
                     const uint32_t xl = compress_to_tile(s, g.x_lo);
                     const bool im_flag = !cplx && imag[a];
-                    out.g_hdr.push_back(xl | ((uint32_t)g.nt << 16) | (im_flag ? 0x80000000u : 0u));
-                    out.g_slot.push_back(g.slot);
+                    bool single = true, hermitian = true;
+                    uint32_t zreg0 = 0;
                     for (int64_t i = g.tb; i < g.tb + g.nt; ++i) {
-                        const uint64_t z_lo = recs[i].z & lomask;
-                        out.t_zl.push_back(compress_to_tile(s, z_lo & L));
-                        out.t_zo.push_back(z_lo & ~L);
+                        const uint32_t zl = compress_to_tile(s, (recs[i].z & lomask) & L);
+                        if (i == g.tb)
+                            zreg0 = zl & regmask;
+                        else if ((zl & regmask) != zreg0)
+                            single = false;
+                        if (!recs[i].herm) hermitian = false;
+                        uint32_t pat = 0;  // bit r = parity(z_reg & r)
+                        for (uint32_t r = 0; r <= regmask; ++r) pat |= (uint32_t)(popc64((zl & regmask) & r) & 1) << r;
+                        out.t_zl.push_back((zl & ~regmask) | (pat << 16));
+                        out.t_zo.push_back((recs[i].z & lomask) & ~L);
                         out.t_cre.push_back(im_flag ? recs[i].im : recs[i].re);
                         out.t_cim.push_back(im_flag ? 0.0 : recs[i].im);
                     }
+                    uint32_t skip = 0;
+                    if (hermitian && !cplx && kxor == 0 && (xl >> PLAN_U_SHIFT) != 0) skip = 1u << (31 - __builtin_clz(xl));
+                    uint32_t pat0 = 0;
+                    for (uint32_t r = 0; r <= regmask; ++r) pat0 |= (uint32_t)(popc64(zreg0 & r) & 1) << r;
+                    out.g_hdr.push_back(xl | ((uint32_t)g.nt << HDR_NT_SHIFT) | (im_flag ? HDR_IMAG : 0u) | (single ? HDR_SINGLE : 0u) |
+                                        (skip ? HDR_HALF : 0u));
+                    out.g_hdr.push_back(skip | (pat0 << HDR_PAT_SHIFT));
+                    out.g_slot.push_back(g.slot);
                     done[take[a]] = 1;
                     --left;
                 }
-                s.group_end = (int32_t)out.g_hdr.size();
+                s.group_end = (int32_t)(out.g_hdr.size() / 2);
                 s.term_end = (int64_t)out.t_zl.size();
                 out.sweeps.push_back(s);
                 if (take.empty()) {  // cannot happen: every group fits an empty sweep

@@ -26,15 +26,29 @@ struct TermView {
     const double* constant = nullptr;  // 2*n_slots
 };
 
-constexpr int PLAN_MAX_TILE_BITS = 15;
+constexpr int PLAN_MAX_TILE_BITS = 13;  // the header keeps 13 bits of tile-local X mask
 constexpr int PLAN_MIN_TILE_BITS = 8;   // below this the direct kernel is used
 constexpr int PLAN_MAX_RUNS = 24;
 constexpr int PLAN_LOW_BITS = 3;        // 8 amplitudes = 128 B (c128) contiguous per gather segment
+constexpr int PLAN_REG_BITS = 3;        // tile-local bits [0, 3) index the 8 rows a thread keeps in registers
+constexpr int PLAN_U_SHIFT = 8;         // tile-local bits >= 8 are warp-uniform (row-block index)
+static_assert(PLAN_REG_BITS == PLAN_LOW_BITS, "register rows are the contiguous low amplitudes");
+
+// group header word a
+constexpr uint32_t HDR_XL_MASK = 0x1fffu;   // bits 0..12: tile-local X mask
+constexpr int HDR_NT_SHIFT = 13;            // bits 13..24: number of terms (<= 4095)
+constexpr uint32_t HDR_NT_MASK = 0xfffu;
+constexpr uint32_t HDR_IMAG = 1u << 25;     // gather coefficients purely imaginary (stored in t_cre)
+constexpr uint32_t HDR_SINGLE = 1u << 26;   // every term has the same z bits on the register rows
+constexpr uint32_t HDR_HALF = 1u << 27;     // Hermitian group with an X bit on a warp-uniform tile bit: <psi|G|psi> may visit half the rows
+// group header word b
+constexpr uint32_t HDR_SKIP_MASK = 0x1fffu; // bits 0..12: the warp-uniform X bit used for the half-visit (0 if none)
+constexpr int HDR_PAT_SHIFT = 16;           // bits 16..23: register-row sign pattern of a SINGLE group
 
 struct PlanLimits {
     int tile_bits = 13;
-    int max_terms = 4096;  // per sweep (shared-memory staging capacity)
-    int max_groups = 1024;
+    int max_terms = 2048;  // per sweep (shared-memory staging capacity)
+    int max_groups = 512;
 };
 
 struct SweepHost {
@@ -66,10 +80,11 @@ struct PlanHost {
     bool use_tiles = false;
     std::vector<ClassHost> classes;  // ascending x_hi
     std::vector<SweepHost> sweeps;
-    // tiled layout (sweep order)
-    std::vector<uint32_t> g_hdr;   // xl (bits 0..15) | nterms (bits 16..30) | imag flag (bit 31)
+    // tiled layout (sweep order); two header words per group, see the HDR_* constants
+    std::vector<uint32_t> g_hdr;
     std::vector<int32_t> g_slot;
-    std::vector<uint32_t> t_zl;    // tile-local z mask
+    std::vector<uint32_t> t_zl;    // tile-local z mask, bits [0, REG_BITS) replaced by nothing (cleared); bits 16..23: sign pattern over the
+                                   // thread's 2^REG_BITS register rows, bit r = parity(z_reg & r)
     std::vector<uint64_t> t_zo;    // shard-local z bits outside the tile
     std::vector<double> t_cre, t_cim;  // gather-form coefficients, rank sign folded; imag groups keep Im in t_cre
     // direct layout (class order, original term order inside a class)

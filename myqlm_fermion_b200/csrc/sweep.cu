@@ -26,14 +26,29 @@ namespace qfe {
 
 constexpr int NT = 512;           // threads per CTA of the tile kernel
 constexpr int NW = NT / 32;
-constexpr int RBITS = 3;          // register-blocked rows per thread: R = 8
-static_assert(PLAN_MIN_TILE_BITS == 5 + RBITS, "a tile must hold at least one full warp row block");
+constexpr int RB = PLAN_REG_BITS; // register-blocked rows per thread: R = 8 = the 8 contiguous low amplitudes
+constexpr int R = 1 << RB;
+constexpr int BLK_STRIDE = R + 1; // shared-memory words per 8-row block: one pad word keeps 128-bit accesses conflict-free
+static_assert(PLAN_MIN_TILE_BITS == 5 + RB, "a tile must hold at least one full warp row block");
+static_assert(PLAN_U_SHIFT == 5 + RB, "warp-uniform tile bits start above the lane and register bits");
 
-enum { MODE_EXPECT = 0, MODE_APPLY = 1, MODE_BATCH = 2 };
+// EXPECT_SAME: <psi|H|psi>, bra tile == ket tile (own rows in registers, Hermitian groups visit half the rows)
+// EXPECT:      <bra|H|ket> accumulated as rows of H|ket> then dotted with the bra rows
+// APPLY:       y (+)= H|ket>
+// BATCH:       one value per group (operator pools): <bra| G_g |ket>
+enum { MODE_EXPECT = 0, MODE_APPLY = 1, MODE_BATCH = 2, MODE_EXPECT_SAME = 3 };
 
 template <typename real_t> struct CplxOf;
 template <> struct CplxOf<double> { using type = double2; };
 template <> struct CplxOf<float> { using type = float2; };
+
+// one staged term: coefficient (sign of the z bits outside the tile folded in per tile), the z bits on
+// lane / row-block positions, and the sign pattern over the 8 register rows (bits 16..23)
+template <typename real_t, bool CPLX> struct TermRec;
+template <> struct __align__(16) TermRec<double, false> { double c; uint32_t zp; uint32_t pad; };
+template <> struct __align__(16) TermRec<double, true> { double c; double ci; uint32_t zp; uint32_t pad[3]; };
+template <> struct __align__(8) TermRec<float, false> { float c; uint32_t zp; };
+template <> struct __align__(16) TermRec<float, true> { float c; float ci; uint32_t zp; uint32_t pad; };
 
 struct SweepArgs {
     const void* ket;
@@ -56,22 +71,18 @@ struct SweepArgs {
 };
 
 struct SmemLayout {
-    size_t cre, cim, zp, hdr, spread, acc, red, total;
+    size_t rec, hdr, spread, acc, red, total;
 };
 
 __host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~size_t(15); }
 
-__host__ __device__ inline SmemLayout smem_layout(int k, int n_terms, int n_groups, size_t real_bytes, bool cplx, bool batch) {
+__host__ __device__ inline SmemLayout smem_layout(int k, int n_terms, int n_groups, size_t cplx_bytes, size_t rec_bytes, bool batch) {
     SmemLayout L;
-    size_t off = (size_t(1) << k) * 2 * real_bytes;
-    L.cre = off;
-    off += align16((size_t)n_terms * real_bytes);
-    L.cim = off;
-    if (cplx) off += align16((size_t)n_terms * real_bytes);
-    L.zp = off;
-    off += align16((size_t)n_terms * 4);
+    size_t off = align16((size_t(1) << (k - RB)) * BLK_STRIDE * cplx_bytes);
+    L.rec = off;
+    off += align16((size_t)n_terms * rec_bytes);
     L.hdr = off;
-    off += align16((size_t)n_groups * 4);
+    off += align16((size_t)n_groups * 8);
     L.spread = off;
     off += 128 * 8;
     L.acc = off;
@@ -115,30 +126,104 @@ __device__ __forceinline__ float2 ld_stream(const float2* p) {
     return v;
 }
 
-// w += (flag ? -c : c).  -c differs from c only in the sign bit of its high word, so the select
-// is ONE 32-bit SEL on the high word (the plain C++ conditional costs two selects on the 64-bit sum).
-__device__ __forceinline__ void add_signed(double& w, double c, bool flag) {
-    const int hi = __double2hiint(c), lo = __double2loint(c);
-    w += __hiloint2double(flag ? (hi ^ (int)0x80000000) : hi, lo);
+// value with its sign bit XORed by bit 31 of `flip` (one 32-bit LOP on the high word)
+__device__ __forceinline__ double flip_sign(double c, uint32_t flip) {
+    return __hiloint2double(__double2hiint(c) ^ (int)(flip & 0x80000000u), __double2loint(c));
 }
-__device__ __forceinline__ void add_signed(float& w, float c, bool flag) {
-    w += __int_as_float(flag ? (__float_as_int(c) ^ (int)0x80000000) : __float_as_int(c));
+__device__ __forceinline__ float flip_sign(float c, uint32_t flip) { return __int_as_float(__float_as_int(c) ^ (int)(flip & 0x80000000u)); }
+
+// shared-memory word of tile-local index j: 8-row blocks padded to 9 words
+__device__ __forceinline__ uint32_t tile_word(uint32_t j) { return (j >> RB) * BLK_STRIDE + (j & (R - 1)); }
+
+// Row work of one group for the thread's 8 rows; K = the group's X bits on the register rows (compile time, so
+// that the partner row r ^ K of row r is a fixed register / fixed address offset).
+template <typename real_t, bool CPLX, int MODE, int K>
+__device__ __forceinline__ void group_rows(const typename CplxOf<real_t>::type* __restrict__ pblk, const real_t (&W)[R], const real_t (&Wi)[R],
+                                           const bool imag, const bool half, const typename CplxOf<real_t>::type (&own)[R],
+                                           real_t (&acc_re)[R], real_t (&acc_im)[R], double& e_re, double& e_im, double& e_half) {
+    using cplx_t = typename CplxOf<real_t>::type;
+    if (MODE == MODE_EXPECT_SAME) {
+        if (half) {
+            // Hermitian group: sum over the pair (b, b^x) = 2 Re(conj(psi_b) W psi_p); only rows with the skip bit clear get here
+            real_t s = (real_t)0;
+            if (!imag) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const cplx_t p = pblk[r ^ K];
+                    s += W[r] * (own[r].x * p.x + own[r].y * p.y);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const cplx_t p = pblk[r ^ K];
+                    s += W[r] * (own[r].y * p.x - own[r].x * p.y);  // Re(i w conj(psi_b) psi_p) = -w Im(conj(psi_b) psi_p)
+                }
+            }
+            e_half += (double)s;
+        } else {
+            real_t sr = (real_t)0, si = (real_t)0;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const cplx_t p = pblk[r ^ K];
+                const real_t cr = own[r].x * p.x + own[r].y * p.y;  // conj(psi_b) psi_p
+                const real_t ci = own[r].x * p.y - own[r].y * p.x;
+                if (CPLX) {
+                    sr += W[r] * cr - Wi[r] * ci;
+                    si += W[r] * ci + Wi[r] * cr;
+                } else if (imag) {
+                    sr -= W[r] * ci;
+                    si += W[r] * cr;
+                } else {
+                    sr += W[r] * cr;
+                    si += W[r] * ci;
+                }
+            }
+            e_re += (double)sr;
+            e_im += (double)si;
+        }
+    } else {
+        real_t sr = (real_t)0, si = (real_t)0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const cplx_t p = pblk[r ^ K];
+            real_t t_re, t_im;
+            if (CPLX) {
+                t_re = W[r] * p.x - Wi[r] * p.y;
+                t_im = W[r] * p.y + Wi[r] * p.x;
+            } else if (imag) {
+                t_re = -W[r] * p.y;
+                t_im = W[r] * p.x;
+            } else {
+                t_re = W[r] * p.x;
+                t_im = W[r] * p.y;
+            }
+            if (MODE == MODE_BATCH) {
+                sr += own[r].x * t_re + own[r].y * t_im;  // conj(bra) * t
+                si += own[r].x * t_im - own[r].y * t_re;
+            } else {
+                acc_re[r] += t_re;
+                acc_im[r] += t_im;
+            }
+        }
+        if (MODE == MODE_BATCH) {
+            e_re = (double)sr;
+            e_im = (double)si;
+        }
+    }
 }
 
-template <typename real_t, int RB, bool CPLX, int MODE>
+template <typename real_t, bool CPLX, int MODE>
 __global__ void __launch_bounds__(NT, 1) tile_sweep_kernel(const __grid_constant__ SweepArgs a) {
     using cplx_t = typename CplxOf<real_t>::type;
-    constexpr int R = 1 << RB;
+    using rec_t = TermRec<real_t, CPLX>;
     extern __shared__ __align__(16) unsigned char smem[];
     const int k = a.k;
     const uint32_t tile_amps = 1u << k;
     const int nT = a.n_terms, nG = a.n_groups;
-    const SmemLayout L = smem_layout(k, nT, nG, sizeof(real_t), CPLX, MODE == MODE_BATCH);
+    const SmemLayout L = smem_layout(k, nT, nG, sizeof(cplx_t), sizeof(rec_t), MODE == MODE_BATCH);
     cplx_t* tile = reinterpret_cast<cplx_t*>(smem);
-    real_t* s_cre = reinterpret_cast<real_t*>(smem + L.cre);
-    real_t* s_cim = reinterpret_cast<real_t*>(smem + L.cim);
-    uint32_t* s_zp = reinterpret_cast<uint32_t*>(smem + L.zp);
-    uint32_t* s_hdr = reinterpret_cast<uint32_t*>(smem + L.hdr);
+    rec_t* s_rec = reinterpret_cast<rec_t*>(smem + L.rec);
+    uint2* s_hdr = reinterpret_cast<uint2*>(smem + L.hdr);
     uint64_t* s_spread = reinterpret_cast<uint64_t*>(smem + L.spread);
     double2* s_acc = reinterpret_cast<double2*>(smem + L.acc);
     double2* s_red = reinterpret_cast<double2*>(smem + L.red);
@@ -149,23 +234,16 @@ __global__ void __launch_bounds__(NT, 1) tile_sweep_kernel(const __grid_constant
     cplx_t* __restrict__ yout = reinterpret_cast<cplx_t*>(a.out_vec);
 
     // ---- once per CTA: tile-independent tables ------------------------------------------------
-    for (int t = tid; t < nT; t += NT) {
-        const uint32_t zl = a.t_zl[t];
-        const uint32_t zreg = (zl >> 5) & (R - 1);
-        uint32_t pat = 0;  // bit r = parity(zreg & r): sign pattern over the thread's R rows
-#pragma unroll
-        for (int r = 0; r < R; ++r) pat |= (uint32_t)(__popc(zreg & r) & 1) << r;
-        s_zp[t] = (zl & ~((uint32_t)(R - 1) << 5)) | (pat << 16);
-    }
-    for (int g = tid; g < nG; g += NT) s_hdr[g] = a.g_hdr[g];
+    for (int g = tid; g < nG; g += NT) s_hdr[g] = make_uint2(a.g_hdr[2 * g], a.g_hdr[2 * g + 1]);
     for (int i = tid; i < 128; i += NT) s_spread[i] = a.spread[i];
+    for (int t = tid; t < nT; t += NT) s_rec[t].zp = a.t_zl[t];
     if (MODE == MODE_BATCH)
         for (int i = tid; i < NW * nG; i += NT) s_acc[i] = make_double2(0.0, 0.0);
 
     const int low = a.low_bits;
     const uint32_t lowmask = (1u << low) - 1u;
-    const int rows = 1 << (k - 5 - RB);
-    double e_re = 0.0, e_im = 0.0;
+    const int row_blocks = 1 << (k - 5 - RB);  // warp-level row blocks of 256 amplitudes
+    double e_re = 0.0, e_im = 0.0, e_half = 0.0;
 
     for (unsigned long long tile_id = blockIdx.x; tile_id < a.n_tiles; tile_id += gridDim.x) {
         // shard position of the tile: deposit the tile number into the bits outside the tile mask
@@ -195,108 +273,122 @@ __global__ void __launch_bounds__(NT, 1) tile_sweep_kernel(const __grid_constant
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const uint32_t idx = i0 + u * NT;
-                    if (idx < tile_amps) tile[idx] = v[u];
+                    if (idx < tile_amps) tile[tile_word(idx)] = v[u];
                 }
             }
             // coefficients with the sign of the z bits outside the tile (constant over the tile)
             for (int t = tid; t < nT; t += NT) {
                 const bool neg = __popcll(a.t_zo[t] & base) & 1;
                 const double cr = a.t_cre[t];
-                s_cre[t] = (real_t)(neg ? -cr : cr);
-                if (CPLX) {
+                s_rec[t].c = (real_t)(neg ? -cr : cr);
+                if constexpr (CPLX) {
                     const double ci = a.t_cim[t];
-                    s_cim[t] = (real_t)(neg ? -ci : ci);
+                    s_rec[t].ci = (real_t)(neg ? -ci : ci);
                 }
             }
         }
         __syncthreads();
 
-        for (int u = warp; u < rows; u += NW) {
-            const uint32_t jrow = ((uint32_t)u << (5 + RB)) | (uint32_t)lane;
+        for (int u = warp; u < row_blocks; u += NW) {
+            const uint32_t blk = ((uint32_t)u << 5) | (uint32_t)lane;  // 8-row block of this thread
+            const uint32_t jhi = blk << RB;                            // tile-local index of row 0 (lane and row-block bits)
             real_t acc_re[R], acc_im[R];
+            cplx_t own[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) acc_re[r] = acc_im[r] = (real_t)0;
-            cplx_t brav[R];
-            if (MODE == MODE_BATCH) {
+            if (MODE == MODE_EXPECT_SAME) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) own[r] = tile[blk * BLK_STRIDE + r];
+            } else if (MODE == MODE_BATCH) {
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    const uint32_t j = jrow | ((uint32_t)r << 5);
-                    if (a.same_tile)
-                        brav[r] = tile[j];
-                    else
-                        brav[r] = bra[base | (j & lowmask) | s_spread[(j >> low) & 63] | s_spread[64 + ((j >> (low + 6)) & 63)]];
+                    if (a.same_tile) {
+                        own[r] = tile[blk * BLK_STRIDE + r];
+                    } else {
+                        const uint32_t j = jhi | (uint32_t)r;
+                        own[r] = bra[base | (j & lowmask) | s_spread[(j >> low) & 63] | s_spread[64 + ((j >> (low + 6)) & 63)]];
+                    }
                 }
             }
             int tb = 0;
             for (int g = 0; g < nG; ++g) {
-                const uint32_t hdr = s_hdr[g];
-                const uint32_t xl = hdr & 0xffffu;
-                const int nt = (int)((hdr >> 16) & 0x7fffu);
-                const bool imag = hdr >> 31;
-                real_t W[R], Wi[R];  // W_x(row) = sum_t c_t (-1)^{|z_t & row|}
+                const uint2 hdr = s_hdr[g];
+                const uint32_t xl = hdr.x & HDR_XL_MASK;
+                const int nt = (int)((hdr.x >> HDR_NT_SHIFT) & HDR_NT_MASK);
+                const bool imag = hdr.x & HDR_IMAG;
+                bool half = false;
+                if (MODE == MODE_EXPECT_SAME) {
+                    half = hdr.x & HDR_HALF;
+                    if (half && (jhi & hdr.y & HDR_SKIP_MASK)) {  // warp-uniform: the partner row block handles this pair
+                        tb += nt;
+                        continue;
+                    }
+                }
+                real_t W[R], Wi[R];  // W(row) = sum_t c_t (-1)^{|z_t & row|}
+                if (!CPLX && (hdr.x & HDR_SINGLE)) {
+                    // all terms share their z bits on the register rows: one signed sum, then the group's row pattern
+                    real_t S = (real_t)0;
+                    for (int t = tb; t < tb + nt; ++t) {
+                        const rec_t rec = s_rec[t];
+                        S += flip_sign(rec.c, (uint32_t)__popc(rec.zp & jhi) << 31);
+                    }
+                    const uint32_t pat = hdr.y >> HDR_PAT_SHIFT;
 #pragma unroll
-                for (int r = 0; r < R; ++r) W[r] = Wi[r] = (real_t)0;
-                for (int t = tb; t < tb + nt; ++t) {
-                    const real_t c = s_cre[t];
-                    const uint32_t zp = s_zp[t];
-                    // sign bit of row r: parity of z over (lane, row) bits XOR the register pattern
-                    const uint32_t m = (zp >> 16) ^ (0u - (uint32_t)(__popc(zp & jrow) & 1));
+                    for (int r = 0; r < R; ++r) {
+                        W[r] = flip_sign(S, pat << (31 - r));
+                        Wi[r] = (real_t)0;
+                    }
+                } else {
 #pragma unroll
-                    for (int r = 0; r < R; ++r) add_signed(W[r], c, (m >> r) & 1u);
-                    if (CPLX) {
-                        const real_t ci = s_cim[t];
+                    for (int r = 0; r < R; ++r) W[r] = Wi[r] = (real_t)0;
+                    for (int t = tb; t < tb + nt; ++t) {
+                        const rec_t rec = s_rec[t];
+                        // sign of row r: parity of z over the lane / row-block bits XOR the register-row pattern
+                        const uint32_t m = (rec.zp >> 16) ^ (0u - (uint32_t)(__popc(rec.zp & jhi) & 1));
 #pragma unroll
-                        for (int r = 0; r < R; ++r) add_signed(Wi[r], ci, (m >> r) & 1u);
+                        for (int r = 0; r < R; ++r) W[r] += flip_sign(rec.c, m << (31 - r));
+                        if constexpr (CPLX) {
+#pragma unroll
+                            for (int r = 0; r < R; ++r) Wi[r] += flip_sign(rec.ci, m << (31 - r));
+                        }
                     }
                 }
                 tb += nt;
-                const uint32_t pj = jrow ^ xl;
-                double v_re = 0.0, v_im = 0.0;
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const cplx_t p = tile[pj ^ ((uint32_t)r << 5)];
-                    const real_t w = W[r];
-                    real_t t_re, t_im;
-                    if (CPLX) {
-                        const real_t wi = Wi[r];
-                        t_re = w * p.x - wi * p.y;
-                        t_im = w * p.y + wi * p.x;
-                    } else if (imag) {
-                        t_re = -w * p.y;
-                        t_im = w * p.x;
-                    } else {
-                        t_re = w * p.x;
-                        t_im = w * p.y;
-                    }
-                    if (MODE == MODE_BATCH) {
-                        v_re += (double)brav[r].x * t_re + (double)brav[r].y * t_im;
-                        v_im += (double)brav[r].x * t_im - (double)brav[r].y * t_re;
-                    } else {
-                        acc_re[r] += t_re;
-                        acc_im[r] += t_im;
-                    }
+                const cplx_t* pblk = tile + (blk ^ (xl >> RB)) * BLK_STRIDE;
+                double g_re = 0.0, g_im = 0.0;
+                double& o_re = (MODE == MODE_BATCH) ? g_re : e_re;
+                double& o_im = (MODE == MODE_BATCH) ? g_im : e_im;
+                switch (xl & (R - 1)) {
+                    case 0: group_rows<real_t, CPLX, MODE, 0>(pblk, W, Wi, imag, half, own, acc_re, acc_im, o_re, o_im, e_half); break;
+                    case 1: group_rows<real_t, CPLX, MODE, 1>(pblk, W, Wi, imag, half, own, acc_re, acc_im, o_re, o_im, e_half); break;
+                    case 2: group_rows<real_t, CPLX, MODE, 2>(pblk, W, Wi, imag, half, own, acc_re, acc_im, o_re, o_im, e_half); break;
+                    case 3: group_rows<real_t, CPLX, MODE, 3>(pblk, W, Wi, imag, half, own, acc_re, acc_im, o_re, o_im, e_half); break;
+                    case 4: group_rows<real_t, CPLX, MODE, 4>(pblk, W, Wi, imag, half, own, acc_re, acc_im, o_re, o_im, e_half); break;
+                    case 5: group_rows<real_t, CPLX, MODE, 5>(pblk, W, Wi, imag, half, own, acc_re, acc_im, o_re, o_im, e_half); break;
+                    case 6: group_rows<real_t, CPLX, MODE, 6>(pblk, W, Wi, imag, half, own, acc_re, acc_im, o_re, o_im, e_half); break;
+                    default: group_rows<real_t, CPLX, MODE, 7>(pblk, W, Wi, imag, half, own, acc_re, acc_im, o_re, o_im, e_half); break;
                 }
                 if (MODE == MODE_BATCH) {
 #pragma unroll
                     for (int d = 16; d > 0; d >>= 1) {
-                        v_re += __shfl_down_sync(0xffffffffu, v_re, d);
-                        v_im += __shfl_down_sync(0xffffffffu, v_im, d);
+                        g_re += __shfl_down_sync(0xffffffffu, g_re, d);
+                        g_im += __shfl_down_sync(0xffffffffu, g_im, d);
                     }
                     if (lane == 0) {  // only this warp writes its own row of s_acc: deterministic
                         double2 cur = s_acc[warp * nG + g];
-                        cur.x += v_re;
-                        cur.y += v_im;
+                        cur.x += g_re;
+                        cur.y += g_im;
                         s_acc[warp * nG + g] = cur;
                     }
                 }
             }
-            if (MODE != MODE_BATCH) {
+            if (MODE == MODE_EXPECT || MODE == MODE_APPLY) {
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    const uint32_t j = jrow | ((uint32_t)r << 5);
+                    const uint32_t j = jhi | (uint32_t)r;
                     const uint64_t gidx = base | (j & lowmask) | s_spread[(j >> low) & 63] | s_spread[64 + ((j >> (low + 6)) & 63)];
                     if (MODE == MODE_EXPECT) {
-                        const cplx_t b = a.same_tile ? tile[j] : bra[gidx];
+                        const cplx_t b = a.same_tile ? tile[blk * BLK_STRIDE + r] : bra[gidx];
                         e_re += (double)b.x * (double)acc_re[r] + (double)b.y * (double)acc_im[r];
                         e_im += (double)b.x * (double)acc_im[r] - (double)b.y * (double)acc_re[r];
                     } else {
@@ -316,8 +408,8 @@ __global__ void __launch_bounds__(NT, 1) tile_sweep_kernel(const __grid_constant
         }
     }
 
-    if (MODE == MODE_EXPECT) {
-        double2 tot = block_reduce_sum(make_double2(e_re, e_im), s_red);
+    if (MODE == MODE_EXPECT || MODE == MODE_EXPECT_SAME) {
+        double2 tot = block_reduce_sum(make_double2(e_re + 2.0 * e_half, e_im), s_red);
         if (tid == 0) a.partials[blockIdx.x] = tot;
     } else if (MODE == MODE_BATCH) {
         __syncthreads();
@@ -454,9 +546,16 @@ static int find_class(const qfe_plan* p, int x_hi) {
     return -1;
 }
 
+static size_t sweep_smem_bytes(const SweepHost& sw, int n_terms, int n_groups, int dtype, bool batch) {
+    const size_t cplx_bytes = dtype == QFE_C128 ? 16 : 8;
+    const size_t rec_bytes = dtype == QFE_C128 ? (sw.complex_w ? sizeof(TermRec<double, true>) : sizeof(TermRec<double, false>))
+                                               : (sw.complex_w ? sizeof(TermRec<float, true>) : sizeof(TermRec<float, false>));
+    return smem_layout(sw.k, n_terms, n_groups, cplx_bytes, rec_bytes, batch).total;
+}
+
 template <typename real_t, bool CPLX, int MODE>
 static int launch_tile(qfe_ctx* ctx, const SweepArgs& args, int grid, size_t smem) {
-    auto kern = tile_sweep_kernel<real_t, RBITS, CPLX, MODE>;
+    auto kern = tile_sweep_kernel<real_t, CPLX, MODE>;
     if (smem > 48 * 1024) QFE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, NT, smem, ctx->stream>>>(args);
     ctx->launches++;
@@ -486,7 +585,7 @@ static int launch_direct(qfe_ctx* ctx, const DirectArgs& args, dim3 grid, int dt
 }
 
 static void fill_sweep_args(const qfe_plan* p, const SweepHost& s, SweepArgs& a) {
-    a.g_hdr = p->g_hdr.as<uint32_t>() + s.group_begin;
+    a.g_hdr = p->g_hdr.as<uint32_t>() + 2 * (size_t)s.group_begin;
     a.t_zl = p->t_zl.as<uint32_t>() + s.term_begin;
     a.t_zo = p->t_zo.as<uint64_t>() + s.term_begin;
     a.t_cre = p->t_cre.as<double>() + s.term_begin;
@@ -543,12 +642,13 @@ static int run_class_reduce(qfe_ctx* ctx, const qfe_plan* p, int ci, const void*
             const int grid = (int)std::min<int64_t>(sw.n_tiles, ctx->sm_count);
             const int n_ranges = batch ? a.n_groups : 1;
             a.partials = ctx->partials.as<double2>();
-            const size_t real_bytes = dtype == QFE_C128 ? 8 : 4;
-            const SmemLayout L = smem_layout(sw.k, a.n_terms, a.n_groups, real_bytes, sw.complex_w, batch);
+            const size_t smem = sweep_smem_bytes(sw, a.n_terms, a.n_groups, dtype, batch);
             if (batch)
-                QFE_TRY(launch_tile_d<MODE_BATCH>(ctx, a, grid, L.total, sw.complex_w, dtype));
+                QFE_TRY(launch_tile_d<MODE_BATCH>(ctx, a, grid, smem, sw.complex_w, dtype));
+            else if (a.same_tile)
+                QFE_TRY(launch_tile_d<MODE_EXPECT_SAME>(ctx, a, grid, smem, sw.complex_w, dtype));
             else
-                QFE_TRY(launch_tile_d<MODE_EXPECT>(ctx, a, grid, L.total, sw.complex_w, dtype));
+                QFE_TRY(launch_tile_d<MODE_EXPECT>(ctx, a, grid, smem, sw.complex_w, dtype));
             reduce_partials<<<(n_ranges + 3) / 4, 128, 0, s>>>(a.partials, n_ranges, grid, d_vals + vpos);
             ctx->launches++;
             QFE_CUDA(cudaGetLastError());
@@ -619,8 +719,8 @@ int qfe_plan_create(qfe_ctx* ctx, const qfe_terms* t, int n_local, int shard, in
         lim.max_terms = 1024;
         lim.max_groups = 128;
     } else {
-        lim.max_terms = 4096;
-        lim.max_groups = 1024;
+        lim.max_terms = 2048;
+        lim.max_groups = 512;
     }
     p->lim = lim;
     TermView v;
@@ -749,8 +849,7 @@ int qfe_apply_class(qfe_ctx* ctx, const qfe_plan* p, int x_hi, const void* ket, 
             a.same_tile = 0;
             a.accumulate = (si == cls.sweep_begin) ? (accumulate ? 1 : 0) : 1;
             const int grid = (int)std::min<int64_t>(sw.n_tiles, ctx->sm_count);
-            const SmemLayout L = smem_layout(sw.k, a.n_terms, a.n_groups, dtype == QFE_C128 ? 8 : 4, sw.complex_w, false);
-            QFE_TRY(launch_tile_d<MODE_APPLY>(ctx, a, grid, L.total, sw.complex_w, dtype));
+            QFE_TRY(launch_tile_d<MODE_APPLY>(ctx, a, grid, sweep_smem_bytes(sw, a.n_terms, a.n_groups, dtype, false), sw.complex_w, dtype));
         }
     } else {
         DirectArgs a;

@@ -101,6 +101,18 @@ class Engine:
         check(self.lib.qfe_ctx_launch_count(self.ctx, C.byref(v)))
         return v.value
 
+    def use_torch_stream(self) -> None:
+        """Launch every libqfe kernel on torch's current stream (so that ``torch.cuda.Event`` brackets
+        them).  The legacy default stream cannot be handed over as a handle: a fresh torch stream is
+        made current in that case."""
+        torch = _torch()
+        cur = torch.cuda.current_stream(self.device)
+        if cur.cuda_stream == 0:
+            cur = torch.cuda.Stream(self.device)
+            torch.cuda.set_stream(cur)
+        self._torch_stream = cur  # keep it alive
+        check(self.lib.qfe_ctx_set_stream(self.ctx, C.c_void_p(cur.cuda_stream)))
+
     def _sync_torch(self) -> None:
         # libqfe runs on its own non-blocking stream: order it after whatever torch queued
         _torch().cuda.current_stream(self.device).synchronize()

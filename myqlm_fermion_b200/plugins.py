@@ -1,0 +1,171 @@
+"""Observable-evaluation surface of the reference's plugins, on device statevectors.
+
+The reference's plugins talk to a QPU through ``self.execute(job).value`` with
+``job = circuit.to_job(observable=O)`` (/root/reference/qat/plugins/adapt_vqe.py:182,
+/root/reference/qat/fermion/vqe.py:53-59, /root/reference/qat/plugins/sequential_optimization.py:96-100).
+State preparation from circuits belongs to the QPU and is not part of this path: here the state
+arrives as a device buffer (a torch CUDA tensor) or as a callable ``params -> state``, and the
+observable evaluations are done by libqfe.
+
+* ``StatevectorQPU.submit(observable, psi) -> Result``      <->  ``qpu.submit(job) -> Result`` for OBS jobs
+* ``AdaptVQEGradients``                                      <->  AdaptVQEPlugin._compute_commutators + the gradient loop
+                                                                 (adapt_vqe.py:50-62, 181-195)
+* ``SeqOptim.optimize``                                      <->  SeqOptim.optimize (sequential_optimization.py:104-146)
+* ``vqe_energy``                                             <->  VQE.fun (vqe.py:53-59)
+"""
+
+from __future__ import annotations
+
+import math
+import warnings
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+
+from .hamiltonians import SpinHamiltonian
+
+
+class Result:
+    """``qat.core.Result`` look-alike: ``value``, ``meta_data`` (dict of strings), ``parameter_map``."""
+
+    def __init__(self, value=None, meta_data=None, parameter_map=None):
+        self.value = value
+        self.meta_data = meta_data if meta_data is not None else {}
+        self.parameter_map = parameter_map
+
+
+class StatevectorQPU:
+    """Evaluates OBS jobs on a given device statevector: ``submit(observable, psi).value = <psi|O|psi>``."""
+
+    def __init__(self, engine=None):
+        from .engine import get_engine
+
+        self.engine = engine or get_engine()
+
+    def _terms(self, observable):
+        if isinstance(observable, SpinHamiltonian):
+            return observable.packed(self.engine)
+        return observable  # PackedTerms / Plan
+
+    def submit(self, observable, psi) -> Result:
+        val = self.engine.expectation(self._terms(observable), psi)
+        return Result(value=val.real if abs(val.imag) <= 1e-12 * max(1.0, abs(val)) else val)
+
+    def submit_batch(self, observables: Sequence, psi) -> List[Result]:
+        """Many observables on ONE state (what the ADAPT / natural-gradient loops do job by job): one batched sweep."""
+        batch = self.engine.concat([self._terms(o) for o in observables])
+        vals = np.atleast_1d(self.engine.expectation(batch, psi))
+        return [Result(value=complex(v)) for v in vals]
+
+
+class AdaptVQEGradients:
+    """Gradient sweep of ADAPT-VQE: ``g_k = -i <psi|[H, tau_k]|psi>`` for every pool operator.
+
+    ``mode="matrix-free"`` (default) evaluates 2 Im <H psi|tau_k|psi> with one H|psi> and one batched
+    pass over the pool; ``mode="commutators"`` follows the reference literally: the observables
+    ``H | tau_k`` are expanded (``_compute_commutators``) and each is measured on the state."""
+
+    def __init__(self, operator_pool: Sequence[SpinHamiltonian], tol_vanishing_grad: float = 1e-3, commutators=None, engine=None, mode: str = "matrix-free"):
+        from .engine import get_engine
+
+        if mode not in ("matrix-free", "commutators"):
+            raise ValueError(f"unknown mode {mode!r}")
+        self.engine = engine or get_engine()
+        self.pool = list(operator_pool)
+        self.tol_vanishing_grad = tol_vanishing_grad
+        self.commutators = commutators
+        self.mode = mode
+        self._pool_terms = None
+        self._h_key = None
+        self._h_terms = None
+
+    @staticmethod
+    def _compute_commutators(observable: SpinHamiltonian, pool: Sequence[SpinHamiltonian]):
+        return [observable | op for op in pool]
+
+    def gradients(self, observable: SpinHamiltonian, psi) -> np.ndarray:
+        eng = self.engine
+        if self.mode == "commutators":
+            if self.commutators is None:
+                self.commutators = self._compute_commutators(observable, self.pool)
+            batch = eng.concat([c.packed(eng) for c in self.commutators])
+            vals = np.atleast_1d(eng.expectation(batch, psi))
+            return np.real(-1j * vals)
+        if self._pool_terms is None:
+            self._pool_terms = eng.concat([op.packed(eng) for op in self.pool])
+        if self._h_key != id(observable):
+            self._h_terms, self._h_key = observable.packed(eng), id(observable)
+        return eng.commutator_gradients(self._h_terms, self._pool_terms, psi)
+
+    def select(self, energy_gradients: np.ndarray):
+        """(operator index or None, gradient norm) as adapt_vqe.py:186-195."""
+        norm = float(np.linalg.norm(energy_gradients))
+        if norm < self.tol_vanishing_grad:
+            warnings.warn("Norm of the energy gradient is below the set threshold. Ending calculation.", stacklevel=2)
+            return None, norm
+        return int(np.argmax(np.abs(energy_gradients))), norm
+
+
+class SeqOptimResult:
+    def __init__(self, x, fun):
+        self.x = x
+        self.fun = fun
+
+
+class SeqOptim:
+    """Rotosolve (sequential_optimization.py:53-146): three energy evaluations per angle and cycle."""
+
+    def __init__(self, ncycles: Optional[int] = 10, coeff: Optional[float] = 1, x0: Optional[np.ndarray] = None, verbose: Optional[bool] = False):
+        self.ncycles_roto = ncycles
+        self.coeff = coeff
+        self.x0 = x0
+        self.verbose = verbose
+        self.n_evaluations = 0
+
+    def optimize(self, var_names: Sequence[str], evaluate: Callable[[dict], float]):
+        """``evaluate(params: dict) -> energy`` plays the role of ``Optimizer.evaluate``."""
+        n_params = len(var_names)
+        x0 = list(self.x0) if self.x0 is not None else list(np.random.random(n_params))
+        params = {var_names[i]: val for i, val in enumerate(x0)}
+
+        def ev(p):
+            self.n_evaluations += 1
+            try:
+                scaled = {k: v * self.coeff for k, v in p.items()}
+            except Exception as exc:
+                raise ValueError("Parameters must be real-valued!") from exc
+            return evaluate(scaled)
+
+        cf = ev(params)
+        for k in range(self.ncycles_roto):
+            if self.verbose:
+                print("-------Optimization cycle #%i-----------" % (k + 1))
+            for d in range(n_params):
+                key = str(var_names[d])
+                plus = dict(params)
+                plus[key] = params[key] + math.pi / 2
+                cf_plus = np.real(ev(plus))
+                minus = dict(params)
+                minus[key] = params[key] - math.pi / 2
+                cf_minus = np.real(ev(minus))
+                new = dict(params)
+                new[key] = params[key] - math.pi / 2 - math.atan2(2 * cf - cf_plus - cf_minus, cf_plus - cf_minus)
+                cf = np.real(ev(new))
+                params = new
+            if self.verbose:
+                print("current cost:", cf)
+        result = SeqOptimResult(params.values(), cf)
+        return result.fun, list(result.x), result
+
+
+def vqe_energy(hamiltonian: SpinHamiltonian, state_routine: Callable, engine=None) -> Callable:
+    """``VQE.fun`` (vqe.py:53-59): theta -> <psi(theta)|H|psi(theta)> with ``state_routine(theta)`` a device state."""
+    from .engine import get_engine
+
+    eng = engine or get_engine()
+    plan = eng.plan(hamiltonian.packed(eng))
+
+    def fun(theta):
+        return eng.energy(plan, state_routine(theta))
+
+    return fun

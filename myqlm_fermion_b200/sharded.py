@@ -1,0 +1,209 @@
+"""Statevector sharded over the ranks of one node: one process per GPU, ``torch.distributed`` for the
+plumbing (NCCL over NVLink/NVSwitch on the GPU box, gloo in the CPU tests).
+
+Rank r holds the 2^(n-g) amplitudes whose g most significant index bits (= qubits 0..g-1, because
+qubit 0 is the MSB: /root/reference/qat/fermion/hamiltonians.py:231-235) equal r.  A Pauli term whose
+X mask has high part x_hi maps shard r onto shard r ^ x_hi, so the terms fall into at most 2^g
+*classes*; class 0 is local, every other class needs ONE pairwise exchange of the shard with rank
+r ^ x_hi (``isend``/``irecv``), after which all sweeps of that class run locally on
+(own shard, partner shard).  Scalars are combined with one all-reduce.
+
+The reference has no distributed path at all; this module is new structure around the same numbers.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+
+def _dist():
+    import torch.distributed as dist
+
+    return dist
+
+
+class ShardedEngine:
+    """Drives a per-rank compute backend (``Engine`` on the GPU box) over the x_hi classes.
+
+    ``backend`` must provide ``plan(terms, n_local, shard)``, ``expectation_class``, ``apply_class``,
+    ``dot``, ``axpy``, ``scale`` and the state constructors; ``Engine`` does.
+    """
+
+    def __init__(self, backend, nqbits: int, group=None):
+        dist = _dist()
+        if not dist.is_initialized():
+            raise RuntimeError("ShardedEngine needs an initialised torch.distributed process group")
+        self.backend = backend
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        g = self.world.bit_length() - 1
+        if 1 << g != self.world:
+            raise ValueError(f"world size {self.world} is not a power of two")
+        if g > nqbits:
+            raise ValueError("more ranks than amplitudes")
+        self.g = g
+        self.nqbits = nqbits
+        self.n_local = nqbits - g
+        self._partner = None
+        self.exchanges = 0
+        self.exchanged_bytes = 0
+
+    # ---- plumbing ------------------------------------------------------------------------------
+    def plan(self, terms):
+        return self.backend.plan(terms, n_local=self.n_local, shard=self.rank)
+
+    def _partner_buffer(self, like):
+        import torch
+
+        if self._partner is None or self._partner.shape != like.shape or self._partner.dtype != like.dtype or self._partner.device != like.device:
+            self._partner = torch.empty_like(like)
+        return self._partner
+
+    def release_buffers(self) -> None:
+        self._partner = None
+
+    def exchange(self, shard, x_hi: int):
+        """Partner shard (rank ^ x_hi) of the vector ``shard`` belongs to; pairwise send/recv."""
+        if x_hi == 0:
+            return shard
+        dist = _dist()
+        import torch
+
+        peer = self.rank ^ x_hi
+        buf = self._partner_buffer(shard)
+        # complex tensors travel as their real view (NCCL has no complex dtype)
+        send_t, recv_t = torch.view_as_real(shard), torch.view_as_real(buf)
+        peer_global = dist.get_global_rank(self.group, peer) if self.group is not None else peer
+        ops = [dist.P2POp(dist.isend, send_t, peer_global, group=self.group), dist.P2POp(dist.irecv, recv_t, peer_global, group=self.group)]
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        if shard.is_cuda:
+            torch.cuda.current_stream(shard.device).synchronize()
+        self.exchanges += 1
+        self.exchanged_bytes += shard.numel() * shard.element_size()
+        return buf
+
+    def allreduce(self, values: np.ndarray) -> np.ndarray:
+        import torch
+
+        dist = _dist()
+        dev = "cuda" if dist.get_backend(self.group) == "nccl" else "cpu"
+        t = torch.from_numpy(np.ascontiguousarray(values, dtype=np.float64)).to(dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t.cpu().numpy()
+
+    # ---- kernel 2 on shards ----------------------------------------------------------------------
+    def expectation(self, plan, ket_shard, bra_shard=None):
+        """<bra|H|ket> of the whole register (identical on every rank)."""
+        bra = ket_shard if bra_shard is None else bra_shard
+        n_slots = plan.terms.n_slots
+        acc = np.zeros(n_slots, dtype=np.complex128)
+        for x_hi in plan.classes:  # the class list is the same on every rank (it depends on the X masks only)
+            partner = self.exchange(ket_shard, x_hi)
+            acc += np.atleast_1d(self.backend.expectation_class(plan, x_hi, bra, partner))
+        tot = self.allreduce(acc.view(np.float64)).view(np.complex128)
+        return complex(tot[0]) if n_slots == 1 else tot
+
+    def energy(self, plan, ket_shard) -> float:
+        return float(np.real(self.expectation(plan, ket_shard)))
+
+    def apply(self, plan, ket_shard, out_shard=None):
+        """This rank's shard of H|ket>."""
+        import torch
+
+        y = torch.empty_like(ket_shard) if out_shard is None else out_shard
+        first = True
+        for x_hi in plan.classes:
+            partner = self.exchange(ket_shard, x_hi)
+            self.backend.apply_class(plan, x_hi, partner, y, accumulate=not first)
+            first = False
+        if first:
+            y.zero_()
+        return y
+
+    def commutator_gradients(self, h_plan, pool_plan, psi_shard, scratch=None) -> np.ndarray:
+        """g_k = -i<psi|[H, tau_k]|psi> = 2 Im <H psi|tau_k|psi> (adapt_vqe.py:181-185), sharded."""
+        phi = self.apply(h_plan, psi_shard, out_shard=scratch)
+        vals = np.atleast_1d(self.expectation(pool_plan, psi_shard, bra_shard=phi))
+        return 2.0 * vals.imag
+
+    # ---- vector helpers ----------------------------------------------------------------------------
+    def dot(self, a_shard, b_shard) -> complex:
+        v = np.array([self.backend.dot(a_shard, b_shard)], dtype=np.complex128)
+        return complex(self.allreduce(v.view(np.float64)).view(np.complex128)[0])
+
+    def random_state(self, dtype=None, seed: int = 0):
+        psi = self.backend.random_state(self.nqbits, dtype=dtype, seed=seed, normalize=False, n_local=self.n_local, shard=self.rank)
+        nrm = self.dot(psi, psi).real
+        self.backend.scale(psi, 1.0 / np.sqrt(nrm))
+        return psi
+
+    def product_state(self, alpha_beta, dtype=None):
+        return self.backend.product_state(self.nqbits, alpha_beta, dtype=dtype, n_local=self.n_local, shard=self.rank)
+
+    # ---- kernel 3 on shards ------------------------------------------------------------------------
+    def ground_state(self, plan, v0_shard=None, max_iter: int = 300, tol: float = 1e-10, dtype=None, want_vector: bool = True, seed: int = 0):
+        """Lanczos on the sharded apply; same recurrence as ``qfe_lanczos`` with the dots all-reduced.
+        Returns (E0, psi0 shard or None, info)."""
+        from scipy.linalg import eigh_tridiagonal
+
+        be = self.backend
+        start = self.random_state(dtype=dtype, seed=seed) if v0_shard is None else v0_shard.clone()
+        nrm = np.sqrt(self.dot(start, start).real)
+        if nrm == 0.0:
+            raise ValueError("start vector has zero norm")
+        be.scale(start, 1.0 / nrm)
+        alpha, beta = [], []
+        theta, y, res, m_done = 0.0, None, 0.0, 0
+
+        def solve(m):
+            a = np.array(alpha[:m])
+            if m == 1:
+                return a[0], np.ones(1)
+            w, v = eigh_tridiagonal(a, np.array(beta[: m - 1]), select="i", select_range=(0, 0))
+            return float(w[0]), v[:, 0]
+
+        for pass_no in range(2 if want_vector else 1):
+            cur = start.clone()
+            prev = None
+            out = None
+            if pass_no == 1:
+                out = cur.clone()
+                be.scale(out, y[0])
+            m_target = max_iter if pass_no == 0 else m_done
+            for j in range(m_target):
+                w = self.apply(plan, cur)
+                if pass_no == 0:
+                    a_j = self.dot(cur, w).real
+                    alpha.append(a_j)
+                else:
+                    a_j = alpha[j]
+                be.axpy(-a_j, cur, w)
+                if prev is not None:
+                    be.axpy(-beta[j - 1], prev, w)
+                if pass_no == 0:
+                    b_j = np.sqrt(max(self.dot(w, w).real, 0.0))
+                    beta.append(b_j)
+                    m = j + 1
+                    m_done = m
+                    tiny = b_j <= 1e-14 * max(1.0, abs(a_j))
+                    if m % 5 == 0 or m == max_iter or tiny:
+                        theta, y = solve(m)
+                        res = abs(b_j * y[m - 1])
+                        if res <= tol * max(1.0, abs(theta)) or tiny:
+                            break
+                else:
+                    b_j = beta[j]
+                    if j + 1 >= m_done:
+                        break
+                if b_j == 0.0:
+                    break
+                be.scale(w, 1.0 / b_j)
+                prev, cur = cur, w
+                if pass_no == 1:
+                    be.axpy(y[j + 1], cur, out)
+            if pass_no == 0:
+                theta, y = solve(m_done)
+                res = abs(beta[m_done - 1] * y[m_done - 1])
+        return theta, (out if want_vector else None), {"iterations": m_done, "residual": res}

@@ -46,6 +46,14 @@ def synthetic_h_integrals(m: int, seed: int = 1234):
     return convert_to_h_integrals(*synthetic_integrals(m, seed))
 
 
+def synthetic_h_integrals_n(n: int, seed: int = 1234):
+    """The generator on n spin-orbitals; an odd n keeps the first n of the 2*ceil(n/2) spin-orbitals."""
+    hpq, hpqrs = synthetic_h_integrals((n + 1) // 2, seed)
+    if n % 2:
+        hpq, hpqrs = np.ascontiguousarray(hpq[:n, :n]), np.ascontiguousarray(hpqrs[:n, :n, :n, :n])
+    return hpq, hpqrs
+
+
 def hubbard_chain_t(ns: int, t: float = -1.0) -> np.ndarray:
     t_mat = np.zeros((ns, ns))
     for i in range(ns - 1):

@@ -15,7 +15,8 @@ using namespace qfe;
 
 extern "C" int plan_emul_run(int n, int64_t T, const uint64_t* x, const uint64_t* z, const double* c, const int32_t* owner, int64_t n_slots,
                              const double* constant, int n_local, int shard, int tile_bits, int max_terms, int max_groups, int x_hi,
-                             const double* bra_, const double* ket_, double* out_slots, double* y_, int64_t* stats /* sweeps, groups, terms, classes */) {
+                             const double* bra_, const double* ket_, double* out_slots, double* y_, int64_t* stats /* sweeps, groups, terms, classes */,
+                             int half_visit) {
     TermView v;
     v.n = n;
     v.T = T;
@@ -41,7 +42,7 @@ extern "C" int plan_emul_run(int n, int64_t T, const uint64_t* x, const uint64_t
     stats[3] = (int64_t)p.classes.size();
     // every group of every class must be covered by exactly one sweep
     {
-        size_t ng_tiled = p.g_hdr.size(), ng_direct = p.dg_slot.size();
+        size_t ng_tiled = p.g_hdr.size() / 2, ng_direct = p.dg_slot.size();
         if (ng_tiled != ng_direct || p.t_zl.size() != p.d_x.size()) return 3;
     }
     for (const ClassHost& cls : p.classes) {
@@ -68,25 +69,45 @@ extern "C" int plan_emul_run(int n, int64_t T, const uint64_t* x, const uint64_t
                         seen[base | pos] = 1;
                     }
                 }
+                // <psi|G|psi> with bra == ket on the same tile may visit half the rows of a Hermitian group (HDR_HALF)
+                const bool same = (bra == ket) && s.ket_xor == 0 && half_visit;
                 for (uint32_t j = 0; j < tile_amps; ++j) {
                     const uint64_t row = base | tile_spread(s, j);
                     int64_t tb = s.term_begin;
                     cplx acc_row(0.0, 0.0);
                     for (int g = s.group_begin; g < s.group_end; ++g) {
-                        const uint32_t hdr = p.g_hdr[g];
-                        const uint32_t xl = hdr & 0xffffu;
-                        const int nt = (int)((hdr >> 16) & 0x7fffu);
-                        const bool imag = hdr >> 31;
+                        const uint32_t ha = p.g_hdr[2 * g], hb = p.g_hdr[2 * g + 1];
+                        const uint32_t xl = ha & HDR_XL_MASK;
+                        const int nt = (int)((ha >> HDR_NT_SHIFT) & HDR_NT_MASK);
+                        const bool imag = ha & HDR_IMAG;
+                        const uint32_t skip = hb & HDR_SKIP_MASK;
+                        if (((ha & HDR_HALF) != 0) != (skip != 0)) return 10;
+                        if (skip && (skip != (1u << (31 - __builtin_clz(xl))) || skip < (1u << PLAN_U_SHIFT))) return 11;  // highest X bit, warp-uniform
                         cplx w(0.0, 0.0);
+                        uint32_t zreg0 = 0;
+                        bool single = true;
                         for (int64_t tt = tb; tt < tb + nt; ++tt) {
-                            const int par = (__builtin_popcount(p.t_zl[tt] & j) + __builtin_popcountll(p.t_zo[tt] & base)) & 1;
+                            const uint32_t zl = p.t_zl[tt] & 0xffffu, pat = (p.t_zl[tt] >> 16) & 0xffu;
+                            if (zl & 7u) return 12;  // register bits live in the pattern only
+                            const uint32_t jr = j & 7u;
+                            const int par = (__builtin_popcount(zl & j) + (int)((pat >> jr) & 1u) + __builtin_popcountll(p.t_zo[tt] & base)) & 1;
+                            if (tt == tb)
+                                zreg0 = pat;
+                            else if (pat != zreg0)
+                                single = false;
                             cplx cc = imag ? cplx(0.0, p.t_cre[tt]) : cplx(p.t_cre[tt], p.t_cim[tt]);
                             w += par ? -cc : cc;
                         }
+                        if (single != ((ha & HDR_SINGLE) != 0)) return 13;
+                        if (single && ((hb >> HDR_PAT_SHIFT) & 0xffu) != zreg0) return 14;
                         tb += nt;
                         const cplx contrib = w * tile[j ^ xl];
                         acc_row += contrib;
-                        out[p.g_slot[g]] += std::conj(bra[row]) * contrib;
+                        if (same && skip) {
+                            if (!(j & skip)) out[p.g_slot[g]] += 2.0 * std::real(std::conj(bra[row]) * contrib);
+                        } else {
+                            out[p.g_slot[g]] += std::conj(bra[row]) * contrib;
+                        }
                     }
                     if (tb != s.term_end) return 8;
                     y[row] += acc_row;
@@ -121,7 +142,7 @@ extern "C" int plan_emul_stats(int n, int64_t T, const uint64_t* x, const uint64
     const char* err = nullptr;
     if (build_plan(v, n_local, shard, lim, p, &err) != 0) return 1;
     stats[0] = (int64_t)p.sweeps.size();
-    stats[1] = (int64_t)p.g_hdr.size();
+    stats[1] = (int64_t)p.g_hdr.size() / 2;
     stats[2] = (int64_t)p.t_zl.size();
     stats[3] = (int64_t)p.classes.size();
     for (size_t i = 0; i < p.sweeps.size() && (int32_t)i < capacity; ++i) groups_per_sweep[i] = p.sweeps[i].group_end - p.sweeps[i].group_begin;

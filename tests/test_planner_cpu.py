@@ -24,12 +24,12 @@ def emul():
     lib.plan_emul_run.restype = C.c_int
     lib.plan_emul_run.argtypes = [
         C.c_int, C.c_int64, P(C.c_uint64), P(C.c_uint64), P(C.c_double), P(C.c_int32), C.c_int64, P(C.c_double),
-        C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, P(C.c_double), P(C.c_double), P(C.c_double), P(C.c_double), P(C.c_int64),
+        C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, P(C.c_double), P(C.c_double), P(C.c_double), P(C.c_double), P(C.c_int64), C.c_int,
     ]
     return lib
 
 
-def _run(lib, n, x, z, c, owner, n_slots, constant, n_local, shard, tile_bits, x_hi, bra, ket, max_terms=4096, max_groups=1024):
+def _run(lib, n, x, z, c, owner, n_slots, constant, n_local, shard, tile_bits, x_hi, bra, ket, max_terms=2048, max_groups=512, half_visit=0):
     x = np.ascontiguousarray(x, dtype=np.uint64)
     z = np.ascontiguousarray(z, dtype=np.uint64)
     c = np.ascontiguousarray(c, dtype=np.complex128)
@@ -42,7 +42,7 @@ def _run(lib, n, x, z, c, owner, n_slots, constant, n_local, shard, tile_bits, x
     rc = lib.plan_emul_run(
         n, len(x), ptr(x, C.c_uint64), ptr(z, C.c_uint64), ptr(c, C.c_double), ptr(owner, C.c_int32), n_slots, ptr(constant, C.c_double),
         n_local, shard, tile_bits, max_terms, max_groups, x_hi, ptr(np.ascontiguousarray(bra), C.c_double), ptr(np.ascontiguousarray(ket), C.c_double),
-        ptr(out, C.c_double), ptr(y, C.c_double), ptr(stats, C.c_int64),
+        ptr(out, C.c_double), ptr(y, C.c_double), ptr(stats, C.c_int64), half_visit,
     )
     assert rc == 0, f"plan_emul_run failed with code {rc}"
     return out, y, stats
@@ -70,6 +70,10 @@ def test_unsharded_plan_reproduces_apply_and_expectation(emul, enc, tile_bits):
     out, y, stats = _run(emul, n, x, z, c, np.zeros(len(x)), 1, [k], n, 0, tile_bits, 0, bra, psi)
     assert np.max(np.abs(y - want_phi)) <= 1e-12 * np.max(np.abs(want_phi))
     assert abs(out[0] - np.vdot(bra, want_phi)) <= 1e-12
+    # <psi|H|psi> with the half-visit of Hermitian groups (what the EXPECT_SAME kernel does)
+    out2, _, _ = _run(emul, n, x, z, c, np.zeros(len(x)), 1, [k], n, 0, tile_bits, 0, psi, psi, half_visit=1)
+    want_e = np.vdot(psi, want_phi)
+    assert abs(out2[0] - want_e.real) <= 1e-12 * abs(want_e) and abs(want_e.imag) <= 1e-12
     n_groups = len(set(x.tolist())) + (0 if 0 in set(x.tolist()) else 1)  # + identity group if no diagonal term
     assert stats[1] == n_groups and stats[2] == len(x) + 1
     assert 1 <= stats[0] <= n_groups
