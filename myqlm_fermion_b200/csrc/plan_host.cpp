@@ -286,38 +286,101 @@ int build_plan(const TermView& t, int n_local, int shard, const PlanLimits& lim,
                 s.complex_w = cplx;
                 s.group_begin = (int32_t)(out.g_hdr.size() / 2);
                 s.term_begin = (int64_t)out.t_zl.size();
+                s.range_begin = (int32_t)(out.r_desc.size() / 2);
                 const uint32_t regmask = (1u << PLAN_REG_BITS) - 1u;
+                // classify every group, then order the sweep's groups by (skip bit, kind, K) so that the kernel
+                // walks homogeneous ranges: whole ranges are skipped / dispatched, not single groups
+                struct GInfo {
+                    size_t gi;
+                    uint32_t xl, word_b;
+                    bool imag;
+                    int kind, K, skipbit;
+                    std::vector<int64_t> order;  // term emit order
+                };
+                std::vector<GInfo> info(take.size());
                 for (size_t a = 0; a < take.size(); ++a) {
                     const Group& g = groups[take[a]];
-                    const uint32_t xl = compress_to_tile(s, g.x_lo);
-                    const bool im_flag = !cplx && imag[a];
+                    GInfo& gi = info[a];
+                    gi.gi = take[a];
+                    gi.xl = compress_to_tile(s, g.x_lo);
+                    gi.imag = !cplx && imag[a];
+                    gi.K = (int)(gi.xl & regmask);
                     bool single = true, hermitian = true;
                     uint32_t zreg0 = 0;
+                    int counts[1 << PLAN_REG_BITS] = {0};
                     for (int64_t i = g.tb; i < g.tb + g.nt; ++i) {
-                        const uint32_t zl = compress_to_tile(s, (recs[i].z & lomask) & L);
+                        const uint32_t zreg = compress_to_tile(s, (recs[i].z & lomask) & L) & regmask;
                         if (i == g.tb)
-                            zreg0 = zl & regmask;
-                        else if ((zl & regmask) != zreg0)
+                            zreg0 = zreg;
+                        else if (zreg != zreg0)
                             single = false;
+                        counts[zreg]++;
                         if (!recs[i].herm) hermitian = false;
+                    }
+                    gi.skipbit = 0;
+                    if (hermitian && !cplx && kxor == 0 && (gi.xl >> PLAN_U_SHIFT) != 0) gi.skipbit = 31 - __builtin_clz(gi.xl);
+                    gi.word_b = 0;
+                    for (int64_t i = g.tb; i < g.tb + g.nt; ++i) gi.order.push_back(i);
+                    if (cplx) {
+                        gi.kind = KIND_GENERIC;
+                    } else if (single && zreg0 == 0) {
+                        gi.kind = KIND_FAST;
+                    } else if (single) {
+                        gi.kind = KIND_SINGLE;
+                        uint32_t pat0 = 0;
+                        for (uint32_t r = 0; r <= regmask; ++r) pat0 |= (uint32_t)(popc64(zreg0 & r) & 1) << r;
+                        gi.word_b = pat0 << HDR_PAT_SHIFT;
+                    } else {
+                        bool small = true;
+                        for (int v = 0; v <= (int)regmask; ++v)
+                            if (counts[v] > 15) small = false;
+                        if (small) {
+                            gi.kind = KIND_MULTI;
+                            for (int v = 0; v <= (int)regmask; ++v) gi.word_b |= (uint32_t)counts[v] << (4 * v);
+                            std::stable_sort(gi.order.begin(), gi.order.end(), [&](int64_t p, int64_t q) {
+                                return (compress_to_tile(s, (recs[p].z & lomask) & L) & regmask) < (compress_to_tile(s, (recs[q].z & lomask) & L) & regmask);
+                            });
+                        } else {
+                            gi.kind = KIND_GENERIC;
+                        }
+                    }
+                }
+                std::vector<size_t> ord(take.size());
+                for (size_t a = 0; a < ord.size(); ++a) ord[a] = a;
+                std::stable_sort(ord.begin(), ord.end(), [&](size_t p, size_t q) {
+                    const GInfo &A = info[p], &B = info[q];
+                    if (A.skipbit != B.skipbit) return A.skipbit < B.skipbit;
+                    return A.kind < B.kind;
+                });
+                for (size_t oi = 0; oi < ord.size(); ++oi) {
+                    const GInfo& gi = info[ord[oi]];
+                    const Group& g = groups[gi.gi];
+                    const uint32_t g_local = (uint32_t)(out.g_hdr.size() / 2 - s.group_begin);
+                    const uint32_t t_local = (uint32_t)(out.t_zl.size() - s.term_begin);
+                    const bool new_range = oi == 0 || info[ord[oi - 1]].skipbit != gi.skipbit || info[ord[oi - 1]].kind != gi.kind;
+                    if (new_range) {
+                        out.r_desc.push_back(g_local | ((g_local + 1) << 16));
+                        out.r_desc.push_back(t_local | ((uint32_t)gi.kind << RNG_KIND_SHIFT) | ((uint32_t)gi.skipbit << RNG_SKIP_SHIFT));
+                    } else {
+                        uint32_t& d0 = out.r_desc[out.r_desc.size() - 2];
+                        d0 = (d0 & 0xffffu) | ((g_local + 1) << 16);
+                    }
+                    for (int64_t i : gi.order) {
+                        const uint32_t zl = compress_to_tile(s, (recs[i].z & lomask) & L);
                         uint32_t pat = 0;  // bit r = parity(z_reg & r)
                         for (uint32_t r = 0; r <= regmask; ++r) pat |= (uint32_t)(popc64((zl & regmask) & r) & 1) << r;
                         out.t_zl.push_back((zl & ~regmask) | (pat << 16));
                         out.t_zo.push_back((recs[i].z & lomask) & ~L);
-                        out.t_cre.push_back(im_flag ? recs[i].im : recs[i].re);
-                        out.t_cim.push_back(im_flag ? 0.0 : recs[i].im);
+                        out.t_cre.push_back(gi.imag ? recs[i].im : recs[i].re);
+                        out.t_cim.push_back(gi.imag ? 0.0 : recs[i].im);
                     }
-                    uint32_t skip = 0;
-                    if (hermitian && !cplx && kxor == 0 && (xl >> PLAN_U_SHIFT) != 0) skip = 1u << (31 - __builtin_clz(xl));
-                    uint32_t pat0 = 0;
-                    for (uint32_t r = 0; r <= regmask; ++r) pat0 |= (uint32_t)(popc64(zreg0 & r) & 1) << r;
-                    out.g_hdr.push_back(xl | ((uint32_t)g.nt << HDR_NT_SHIFT) | (im_flag ? HDR_IMAG : 0u) | (single ? HDR_SINGLE : 0u) |
-                                        (skip ? HDR_HALF : 0u));
-                    out.g_hdr.push_back(skip | (pat0 << HDR_PAT_SHIFT));
+                    out.g_hdr.push_back(tile_word_of(gi.xl) | ((uint32_t)g.nt << HDR_NT_SHIFT) | (gi.imag ? HDR_IMAG : 0u));
+                    out.g_hdr.push_back(gi.word_b);
                     out.g_slot.push_back(g.slot);
-                    done[take[a]] = 1;
+                    done[gi.gi] = 1;
                     --left;
                 }
+                s.range_end = (int32_t)(out.r_desc.size() / 2);
                 s.group_end = (int32_t)(out.g_hdr.size() / 2);
                 s.term_end = (int64_t)out.t_zl.size();
                 out.sweeps.push_back(s);

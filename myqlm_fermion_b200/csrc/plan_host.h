@@ -35,15 +35,29 @@ constexpr int PLAN_U_SHIFT = 8;         // tile-local bits >= 8 are warp-uniform
 static_assert(PLAN_REG_BITS == PLAN_LOW_BITS, "register rows are the contiguous low amplitudes");
 
 // group header word a
-constexpr uint32_t HDR_XL_MASK = 0x1fffu;   // bits 0..12: tile-local X mask
+constexpr uint32_t HDR_XL_MASK = 0x1fffu;   // bits 0..12: tile-local X mask in shared-memory word form, tile_word_of(xl)
 constexpr int HDR_NT_SHIFT = 13;            // bits 13..24: number of terms (<= 4095)
 constexpr uint32_t HDR_NT_MASK = 0xfffu;
 constexpr uint32_t HDR_IMAG = 1u << 25;     // gather coefficients purely imaginary (stored in t_cre)
-constexpr uint32_t HDR_SINGLE = 1u << 26;   // every term has the same z bits on the register rows
-constexpr uint32_t HDR_HALF = 1u << 27;     // Hermitian group with an X bit on a warp-uniform tile bit: <psi|G|psi> may visit half the rows
-// group header word b
-constexpr uint32_t HDR_SKIP_MASK = 0x1fffu; // bits 0..12: the warp-uniform X bit used for the half-visit (0 if none)
-constexpr int HDR_PAT_SHIFT = 16;           // bits 16..23: register-row sign pattern of a SINGLE group
+// group header word b: KIND_SINGLE: bits 16..23 = register-row sign pattern of the group;
+//                      KIND_MULTI: eight 4-bit term counts, one per value of the z bits on the register rows (terms sorted by it)
+constexpr int HDR_PAT_SHIFT = 16;
+
+// A sweep's groups are ordered into *ranges* of equal (skip bit, kind):
+//   skip bit: tile-local index (>= PLAN_U_SHIFT) of the top X bit of a Hermitian group, 0 if none.  <psi|G|psi> on one tile
+//             equals 2 Re over the rows with that bit clear, so row blocks with the bit set skip the whole range;
+//   kind:     how W(row) = sum_t c_t (-1)^{|z_t & row|} is formed for the thread's 8 register rows;
+enum { KIND_FAST = 0,     // no z bit on the register rows: W is the same for the 8 rows
+       KIND_SINGLE = 1,   // all terms share their z bits on the register rows: W = +-S by a group pattern
+       KIND_MULTI = 2,    // terms sorted by their register-row z bits (<= 15 per value): class sums, then an 8-point Walsh-Hadamard
+       KIND_GENERIC = 3   // one signed add per (term, row); the only kind of complex-coefficient sweeps
+};
+// range descriptor: word 0 = first group | (one past the last group) << 16 (sweep-local);
+//                   word 1 = first term (sweep-local) | kind << 16 | skip bit << 24
+constexpr int RNG_KIND_SHIFT = 16, RNG_SKIP_SHIFT = 24;
+
+// shared-memory word of tile-local index j (an involution, linear over GF(2)): see sweep.cu
+inline uint32_t tile_word_of(uint32_t j) { return j ^ ((j >> PLAN_REG_BITS) & ((1u << PLAN_REG_BITS) - 1u)); }
 
 struct PlanLimits {
     int tile_bits = 13;
@@ -64,6 +78,7 @@ struct SweepHost {
     int64_t n_tiles = 0;
     int32_t group_begin = 0, group_end = 0;
     int64_t term_begin = 0, term_end = 0;
+    int32_t range_begin = 0, range_end = 0;
     bool complex_w = false;  // some group mixes real and imaginary gather coefficients
 };
 
@@ -83,6 +98,7 @@ struct PlanHost {
     // tiled layout (sweep order); two header words per group, see the HDR_* constants
     std::vector<uint32_t> g_hdr;
     std::vector<int32_t> g_slot;
+    std::vector<uint32_t> r_desc;  // two words per range
     std::vector<uint32_t> t_zl;    // tile-local z mask, bits [0, REG_BITS) replaced by nothing (cleared); bits 16..23: sign pattern over the
                                    // thread's 2^REG_BITS register rows, bit r = parity(z_reg & r)
     std::vector<uint64_t> t_zo;    // shard-local z bits outside the tile

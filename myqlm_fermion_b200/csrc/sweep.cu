@@ -28,7 +28,9 @@ constexpr int NT = 512;           // threads per CTA of the tile kernel
 constexpr int NW = NT / 32;
 constexpr int RB = PLAN_REG_BITS; // register-blocked rows per thread: R = 8 = the 8 contiguous low amplitudes
 constexpr int R = 1 << RB;
-constexpr int BLK_STRIDE = R + 1; // shared-memory words per 8-row block: one pad word keeps 128-bit accesses conflict-free
+// shared-memory word of tile-local index j is j ^ ((j >> 3) & 7): the 8 rows of a thread sit in one 128 B line, rotated by
+// the low lane bits so that a quarter warp's 128-bit accesses hit 8 distinct bank groups.  The map is linear over GF(2), so
+// the partner j ^ x of row j lives at word(j) ^ word(x): one XOR per group, K (the X bits on the register rows) included.
 static_assert(PLAN_MIN_TILE_BITS == 5 + RB, "a tile must hold at least one full warp row block");
 static_assert(PLAN_U_SHIFT == 5 + RB, "warp-uniform tile bits start above the lane and register bits");
 
@@ -56,11 +58,12 @@ struct SweepArgs {
     void* out_vec;
     double2* partials;
     const uint32_t* g_hdr;
+    const uint32_t* r_desc;
     const uint32_t* t_zl;
     const uint64_t* t_zo;
     const double* t_cre;
     const double* t_cim;
-    int n_groups, n_terms;
+    int n_groups, n_terms, n_ranges;
     int k, low_bits, n_runs;
     int same_tile, accumulate;
     unsigned long long n_tiles;
@@ -71,18 +74,20 @@ struct SweepArgs {
 };
 
 struct SmemLayout {
-    size_t rec, hdr, spread, acc, red, total;
+    size_t rec, hdr, rng, spread, acc, red, total;
 };
 
 __host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~size_t(15); }
 
-__host__ __device__ inline SmemLayout smem_layout(int k, int n_terms, int n_groups, size_t cplx_bytes, size_t rec_bytes, bool batch) {
+__host__ __device__ inline SmemLayout smem_layout(int k, int n_terms, int n_groups, int n_ranges, size_t cplx_bytes, size_t rec_bytes, bool batch) {
     SmemLayout L;
-    size_t off = align16((size_t(1) << (k - RB)) * BLK_STRIDE * cplx_bytes);
+    size_t off = align16((size_t(1) << k) * cplx_bytes);
     L.rec = off;
     off += align16((size_t)n_terms * rec_bytes);
     L.hdr = off;
     off += align16((size_t)n_groups * 8);
+    L.rng = off;
+    off += align16((size_t)n_ranges * 8);
     L.spread = off;
     off += 128 * 8;
     L.acc = off;
@@ -132,52 +137,116 @@ __device__ __forceinline__ double flip_sign(double c, uint32_t flip) {
 }
 __device__ __forceinline__ float flip_sign(float c, uint32_t flip) { return __int_as_float(__float_as_int(c) ^ (int)(flip & 0x80000000u)); }
 
-// shared-memory word of tile-local index j: 8-row blocks padded to 9 words
-__device__ __forceinline__ uint32_t tile_word(uint32_t j) { return (j >> RB) * BLK_STRIDE + (j & (R - 1)); }
+// one shared-memory load per staged term (real-coefficient records)
+__device__ __forceinline__ void load_rec(const TermRec<double, false>* p, double& c, uint32_t& zp) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(p);
+    c = __hiloint2double((int)raw.y, (int)raw.x);
+    zp = raw.z;
+}
+__device__ __forceinline__ void load_rec(const TermRec<float, false>* p, float& c, uint32_t& zp) {
+    const uint2 raw = *reinterpret_cast<const uint2*>(p);
+    c = __uint_as_float(raw.x);
+    zp = raw.y;
+}
+// complex-coefficient sweeps only use the generic path, which reads the fields directly
+__device__ __forceinline__ void load_rec(const TermRec<double, true>* p, double& c, uint32_t& zp) { c = p->c; zp = p->zp; }
+__device__ __forceinline__ void load_rec(const TermRec<float, true>* p, float& c, uint32_t& zp) { c = p->c; zp = p->zp; }
 
-// Row work of one group for the thread's 8 rows; K = the group's X bits on the register rows (compile time, so
-// that the partner row r ^ K of row r is a fixed register / fixed address offset).
-template <typename real_t, bool CPLX, int MODE, int K>
-__device__ __forceinline__ void group_rows(const typename CplxOf<real_t>::type* __restrict__ pblk, const real_t (&W)[R], const real_t (&Wi)[R],
+__device__ __forceinline__ uint32_t tile_word(uint32_t j) { return j ^ ((j >> RB) & (R - 1)); }
+
+// S = sum_t c_t (-1)^{|z_t & jhi|} over terms [t, t + nt): four independent loads, two independent sums
+template <typename rec_t, typename real_t>
+__device__ __forceinline__ real_t signed_sum(const rec_t* __restrict__ s_rec, int t, const int nt, const uint32_t jhi) {
+    real_t S0 = (real_t)0, S1 = (real_t)0;
+    const int te = t + nt;
+    for (; t + 4 <= te; t += 4) {
+        real_t c0, c1, c2, c3;
+        uint32_t z0, z1, z2, z3;
+        load_rec(s_rec + t, c0, z0);
+        load_rec(s_rec + t + 1, c1, z1);
+        load_rec(s_rec + t + 2, c2, z2);
+        load_rec(s_rec + t + 3, c3, z3);
+        c0 = flip_sign(c0, (uint32_t)__popc(z0 & jhi) << 31);
+        c1 = flip_sign(c1, (uint32_t)__popc(z1 & jhi) << 31);
+        c2 = flip_sign(c2, (uint32_t)__popc(z2 & jhi) << 31);
+        c3 = flip_sign(c3, (uint32_t)__popc(z3 & jhi) << 31);
+        S0 += c0 + c2;
+        S1 += c1 + c3;
+    }
+    for (; t < te; ++t) {
+        real_t c;
+        uint32_t z;
+        load_rec(s_rec + t, c, z);
+        S1 += flip_sign(c, (uint32_t)__popc(z & jhi) << 31);
+    }
+    return S0 + S1;
+}
+
+// Row work of one group for the thread's 8 rows; the partner of row r is tile word pw ^ r.
+// UNIFORM: W is the same for the 8 rows (W[0] holds it).
+template <typename real_t, bool CPLX, int MODE, bool UNIFORM>
+__device__ __forceinline__ void group_rows(const typename CplxOf<real_t>::type* __restrict__ tile, const uint32_t pw, const real_t (&W)[R], const real_t (&Wi)[R],
                                            const bool imag, const bool half, const typename CplxOf<real_t>::type (&own)[R],
                                            real_t (&acc_re)[R], real_t (&acc_im)[R], double& e_re, double& e_im, double& e_half) {
     using cplx_t = typename CplxOf<real_t>::type;
-    if (MODE == MODE_EXPECT_SAME) {
-        if (half) {
-            // Hermitian group: sum over the pair (b, b^x) = 2 Re(conj(psi_b) W psi_p); only rows with the skip bit clear get here
-            real_t s = (real_t)0;
-            if (!imag) {
+    if (MODE == MODE_EXPECT_SAME && half) {
+        // Hermitian group: the pair (b, b^x) sums to 2 Re(conj(psi_b) W psi_p); only rows with the skip bit clear get here.
+        // real W: W (a a' + b b');  imaginary W = i w: -w Im(conj(psi_b) psi_p) = w (b a' - a b')
+        real_t s0 = (real_t)0, s1 = (real_t)0;  // two chains keep the FP64 pipe busy
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const cplx_t p = pblk[r ^ K];
-                    s += W[r] * (own[r].x * p.x + own[r].y * p.y);
-                }
+        for (int r = 0; r < R; ++r) {
+            const cplx_t p = tile[pw ^ (uint32_t)r];
+            const real_t u = imag ? p.y : p.x, v = imag ? p.x : p.y;
+            if (UNIFORM) {
+                s0 = fma(imag ? -own[r].x : own[r].x, u, s0);
+                s1 = fma(own[r].y, v, s1);
             } else {
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const cplx_t p = pblk[r ^ K];
-                    s += W[r] * (own[r].y * p.x - own[r].x * p.y);  // Re(i w conj(psi_b) psi_p) = -w Im(conj(psi_b) psi_p)
-                }
+                const real_t t = (imag ? -own[r].x : own[r].x) * u + own[r].y * v;
+                if (r & 1)
+                    s1 = fma(W[r], t, s1);
+                else
+                    s0 = fma(W[r], t, s0);
             }
-            e_half += (double)s;
-        } else {
-            real_t sr = (real_t)0, si = (real_t)0;
+        }
+        e_half += UNIFORM ? (double)(W[0] * (s0 + s1)) : (double)(s0 + s1);
+    } else if (MODE == MODE_EXPECT_SAME || (MODE == MODE_BATCH && UNIFORM)) {
+        // full complex value of sum_r conj(own_r) Wc p_r  (own = ket rows for EXPECT_SAME, bra rows for BATCH)
+        real_t sr = (real_t)0, si = (real_t)0, sr2 = (real_t)0, si2 = (real_t)0;
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const cplx_t p = pblk[r ^ K];
-                const real_t cr = own[r].x * p.x + own[r].y * p.y;  // conj(psi_b) psi_p
+        for (int r = 0; r < R; ++r) {
+            const cplx_t p = tile[pw ^ (uint32_t)r];
+            if (UNIFORM) {  // sum_r conj(own_r) p_r first, the common weight afterwards
+                sr = fma(own[r].x, p.x, sr);
+                sr2 = fma(own[r].y, p.y, sr2);
+                si = fma(own[r].x, p.y, si);
+                si2 = fma(-own[r].y, p.x, si2);
+            } else {
+                const real_t cr = own[r].x * p.x + own[r].y * p.y;
                 const real_t ci = own[r].x * p.y - own[r].y * p.x;
                 if (CPLX) {
                     sr += W[r] * cr - Wi[r] * ci;
                     si += W[r] * ci + Wi[r] * cr;
-                } else if (imag) {
-                    sr -= W[r] * ci;
-                    si += W[r] * cr;
                 } else {
-                    sr += W[r] * cr;
-                    si += W[r] * ci;
+                    sr = fma(W[r], cr, sr);
+                    si = fma(W[r], ci, si);
                 }
             }
+        }
+        sr += sr2;
+        si += si2;
+        if (UNIFORM) {
+            sr *= W[0];
+            si *= W[0];
+        }
+        if (!CPLX && imag) {  // Wc = i W
+            const real_t t = sr;
+            sr = -si;
+            si = t;
+        }
+        if (MODE == MODE_BATCH) {
+            e_re = (double)sr;
+            e_im = (double)si;
+        } else {
             e_re += (double)sr;
             e_im += (double)si;
         }
@@ -185,17 +254,18 @@ __device__ __forceinline__ void group_rows(const typename CplxOf<real_t>::type* 
         real_t sr = (real_t)0, si = (real_t)0;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const cplx_t p = pblk[r ^ K];
+            const cplx_t p = tile[pw ^ (uint32_t)r];
+            const real_t w = UNIFORM ? W[0] : W[r];
             real_t t_re, t_im;
             if (CPLX) {
-                t_re = W[r] * p.x - Wi[r] * p.y;
-                t_im = W[r] * p.y + Wi[r] * p.x;
+                t_re = w * p.x - Wi[r] * p.y;
+                t_im = w * p.y + Wi[r] * p.x;
             } else if (imag) {
-                t_re = -W[r] * p.y;
-                t_im = W[r] * p.x;
+                t_re = -w * p.y;
+                t_im = w * p.x;
             } else {
-                t_re = W[r] * p.x;
-                t_im = W[r] * p.y;
+                t_re = w * p.x;
+                t_im = w * p.y;
             }
             if (MODE == MODE_BATCH) {
                 sr += own[r].x * t_re + own[r].y * t_im;  // conj(bra) * t
@@ -212,6 +282,94 @@ __device__ __forceinline__ void group_rows(const typename CplxOf<real_t>::type* 
     }
 }
 
+// All groups of one range (same skip bit and kind) for the thread's 8 rows.
+template <typename real_t, bool CPLX, int MODE, int KIND>
+__device__ __forceinline__ void process_range(const typename CplxOf<real_t>::type* __restrict__ tile, const TermRec<real_t, CPLX>* __restrict__ s_rec,
+                                              const uint2* __restrict__ s_hdr, double2* __restrict__ s_acc_warp, const int g0, const int g1, int tb,
+                                              const uint32_t w0, const uint32_t jhi, const bool half,
+                                              const typename CplxOf<real_t>::type (&own)[R], real_t (&acc_re)[R], real_t (&acc_im)[R],
+                                              double& e_re, double& e_im, double& e_half) {
+    using cplx_t = typename CplxOf<real_t>::type;
+    using rec_t = TermRec<real_t, CPLX>;
+    for (int g = g0; g < g1; ++g) {
+        const uint2 hdr = s_hdr[g];
+        const uint32_t pw = w0 ^ (hdr.x & HDR_XL_MASK);  // header keeps the X mask already in word form
+        const int nt = (int)((hdr.x >> HDR_NT_SHIFT) & HDR_NT_MASK);
+        const bool imag = hdr.x & HDR_IMAG;
+        real_t W[R], Wi[R];  // W(row) = sum_t c_t (-1)^{|z_t & row|}
+#pragma unroll
+        for (int r = 0; r < R; ++r) Wi[r] = (real_t)0;
+        if (KIND == KIND_FAST) {
+            W[0] = signed_sum<rec_t, real_t>(s_rec, tb, nt, jhi);
+#pragma unroll
+            for (int r = 1; r < R; ++r) W[r] = W[0];
+        } else if (KIND == KIND_SINGLE) {
+            const real_t S = signed_sum<rec_t, real_t>(s_rec, tb, nt, jhi);
+            const uint32_t pat = hdr.y >> HDR_PAT_SHIFT;
+#pragma unroll
+            for (int r = 0; r < R; ++r) W[r] = flip_sign(S, pat << (31 - r));
+        } else if (KIND == KIND_MULTI) {
+            // class sums over the terms sharing their register-row z bits, then W = H_8 S (in-place butterflies)
+            int t = tb;
+#pragma unroll
+            for (int v = 0; v < R; ++v) {
+                const int nv = (int)((hdr.y >> (4 * v)) & 15u);
+                real_t S = (real_t)0;
+                for (int i = 0; i < nv; ++i, ++t) {
+                    real_t c;
+                    uint32_t z;
+                    load_rec(s_rec + t, c, z);
+                    S += flip_sign(c, (uint32_t)__popc(z & jhi) << 31);
+                }
+                W[v] = S;
+            }
+#pragma unroll
+            for (int bit = 1; bit < R; bit <<= 1) {
+#pragma unroll
+                for (int v = 0; v < R; ++v) {
+                    if (!(v & bit)) {
+                        const real_t a = W[v], b = W[v | bit];
+                        W[v] = a + b;
+                        W[v | bit] = a - b;
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; ++r) W[r] = (real_t)0;
+            for (int t = tb; t < tb + nt; ++t) {
+                const rec_t rec = s_rec[t];
+                // sign of row r: parity of z over the lane / row-block bits XOR the register-row pattern
+                const uint32_t m = (rec.zp >> 16) ^ (0u - (uint32_t)(__popc(rec.zp & jhi) & 1));
+#pragma unroll
+                for (int r = 0; r < R; ++r) W[r] += flip_sign(rec.c, m << (31 - r));
+                if constexpr (CPLX) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) Wi[r] += flip_sign(rec.ci, m << (31 - r));
+                }
+            }
+        }
+        tb += nt;
+        if (MODE == MODE_BATCH) {
+            double g_re = 0.0, g_im = 0.0;
+            group_rows<real_t, CPLX, MODE, KIND == KIND_FAST>(tile, pw, W, Wi, imag, false, own, acc_re, acc_im, g_re, g_im, e_half);
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                g_re += __shfl_down_sync(0xffffffffu, g_re, d);
+                g_im += __shfl_down_sync(0xffffffffu, g_im, d);
+            }
+            if ((threadIdx.x & 31) == 0) {  // only this warp writes its own row of the accumulators: deterministic
+                double2 cur = s_acc_warp[g];
+                cur.x += g_re;
+                cur.y += g_im;
+                s_acc_warp[g] = cur;
+            }
+        } else {
+            group_rows<real_t, CPLX, MODE, KIND == KIND_FAST>(tile, pw, W, Wi, imag, half, own, acc_re, acc_im, e_re, e_im, e_half);
+        }
+    }
+}
+
 template <typename real_t, bool CPLX, int MODE>
 __global__ void __launch_bounds__(NT, 1) tile_sweep_kernel(const __grid_constant__ SweepArgs a) {
     using cplx_t = typename CplxOf<real_t>::type;
@@ -219,11 +377,12 @@ __global__ void __launch_bounds__(NT, 1) tile_sweep_kernel(const __grid_constant
     extern __shared__ __align__(16) unsigned char smem[];
     const int k = a.k;
     const uint32_t tile_amps = 1u << k;
-    const int nT = a.n_terms, nG = a.n_groups;
-    const SmemLayout L = smem_layout(k, nT, nG, sizeof(cplx_t), sizeof(rec_t), MODE == MODE_BATCH);
+    const int nT = a.n_terms, nG = a.n_groups, nR = a.n_ranges;
+    const SmemLayout L = smem_layout(k, nT, nG, nR, sizeof(cplx_t), sizeof(rec_t), MODE == MODE_BATCH);
     cplx_t* tile = reinterpret_cast<cplx_t*>(smem);
     rec_t* s_rec = reinterpret_cast<rec_t*>(smem + L.rec);
     uint2* s_hdr = reinterpret_cast<uint2*>(smem + L.hdr);
+    uint2* s_rng = reinterpret_cast<uint2*>(smem + L.rng);
     uint64_t* s_spread = reinterpret_cast<uint64_t*>(smem + L.spread);
     double2* s_acc = reinterpret_cast<double2*>(smem + L.acc);
     double2* s_red = reinterpret_cast<double2*>(smem + L.red);
@@ -235,6 +394,7 @@ __global__ void __launch_bounds__(NT, 1) tile_sweep_kernel(const __grid_constant
 
     // ---- once per CTA: tile-independent tables ------------------------------------------------
     for (int g = tid; g < nG; g += NT) s_hdr[g] = make_uint2(a.g_hdr[2 * g], a.g_hdr[2 * g + 1]);
+    for (int g = tid; g < nR; g += NT) s_rng[g] = make_uint2(a.r_desc[2 * g], a.r_desc[2 * g + 1]);
     for (int i = tid; i < 128; i += NT) s_spread[i] = a.spread[i];
     for (int t = tid; t < nT; t += NT) s_rec[t].zp = a.t_zl[t];
     if (MODE == MODE_BATCH)
@@ -289,98 +449,59 @@ __global__ void __launch_bounds__(NT, 1) tile_sweep_kernel(const __grid_constant
         }
         __syncthreads();
 
-        for (int u = warp; u < row_blocks; u += NW) {
-            const uint32_t blk = ((uint32_t)u << 5) | (uint32_t)lane;  // 8-row block of this thread
-            const uint32_t jhi = blk << RB;                            // tile-local index of row 0 (lane and row-block bits)
+        // Row blocks are dealt to warps in complementary pairs (u, ~u): a Hermitian range is skipped by the row blocks that
+        // have its top X bit set, so block u and its complement together always carry the same amount of work.
+        for (int it = warp; it < row_blocks; it += NW) {
+            const int half_rb = row_blocks >> 1;
+            const int u = (row_blocks == 1) ? 0 : ((it < half_rb) ? it : (row_blocks - 1 - (it - half_rb)));
+            const uint32_t jhi = (((uint32_t)u << 5) | (uint32_t)lane) << RB;  // tile-local index of row 0 (lane and row-block bits)
+            const uint32_t w0 = tile_word(jhi);                                // its shared-memory word; row r is at w0 ^ r
             real_t acc_re[R], acc_im[R];
             cplx_t own[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) acc_re[r] = acc_im[r] = (real_t)0;
             if (MODE == MODE_EXPECT_SAME) {
 #pragma unroll
-                for (int r = 0; r < R; ++r) own[r] = tile[blk * BLK_STRIDE + r];
+                for (int r = 0; r < R; ++r) own[r] = tile[w0 ^ (uint32_t)r];
             } else if (MODE == MODE_BATCH) {
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     if (a.same_tile) {
-                        own[r] = tile[blk * BLK_STRIDE + r];
+                        own[r] = tile[w0 ^ (uint32_t)r];
                     } else {
                         const uint32_t j = jhi | (uint32_t)r;
                         own[r] = bra[base | (j & lowmask) | s_spread[(j >> low) & 63] | s_spread[64 + ((j >> (low + 6)) & 63)]];
                     }
                 }
             }
-            int tb = 0;
-            for (int g = 0; g < nG; ++g) {
-                const uint2 hdr = s_hdr[g];
-                const uint32_t xl = hdr.x & HDR_XL_MASK;
-                const int nt = (int)((hdr.x >> HDR_NT_SHIFT) & HDR_NT_MASK);
-                const bool imag = hdr.x & HDR_IMAG;
+            double2* s_acc_warp = s_acc + (size_t)warp * nG;
+            for (int ri = 0; ri < nR; ++ri) {
+                const uint2 d = s_rng[ri];
+                const uint32_t skipbit = d.y >> RNG_SKIP_SHIFT;
                 bool half = false;
                 if (MODE == MODE_EXPECT_SAME) {
-                    half = hdr.x & HDR_HALF;
-                    if (half && (jhi & hdr.y & HDR_SKIP_MASK)) {  // warp-uniform: the partner row block handles this pair
-                        tb += nt;
-                        continue;
-                    }
+                    half = skipbit != 0;
+                    if (half && ((jhi >> skipbit) & 1u)) continue;  // warp-uniform: the partner row block handles these pairs
                 }
-                real_t W[R], Wi[R];  // W(row) = sum_t c_t (-1)^{|z_t & row|}
-                if (!CPLX && (hdr.x & HDR_SINGLE)) {
-                    // all terms share their z bits on the register rows: one signed sum, then the group's row pattern
-                    real_t S = (real_t)0;
-                    for (int t = tb; t < tb + nt; ++t) {
-                        const rec_t rec = s_rec[t];
-                        S += flip_sign(rec.c, (uint32_t)__popc(rec.zp & jhi) << 31);
-                    }
-                    const uint32_t pat = hdr.y >> HDR_PAT_SHIFT;
-#pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        W[r] = flip_sign(S, pat << (31 - r));
-                        Wi[r] = (real_t)0;
-                    }
+                const int g0 = (int)(d.x & 0xffffu), g1 = (int)(d.x >> 16), t0 = (int)(d.y & 0xffffu);
+#define QFE_RANGE(KIND_)                                                                                                                 \
+    case KIND_:                                                                                                                          \
+        process_range<real_t, CPLX, MODE, KIND_>(tile, s_rec, s_hdr, s_acc_warp, g0, g1, t0, w0, jhi, half, own, acc_re, acc_im, e_re, e_im, \
+                                                 e_half);                                                                                \
+        break;
+                if constexpr (CPLX) {
+                    process_range<real_t, CPLX, MODE, KIND_GENERIC>(tile, s_rec, s_hdr, s_acc_warp, g0, g1, t0, w0, jhi, half, own, acc_re, acc_im,
+                                                                    e_re, e_im, e_half);
                 } else {
-#pragma unroll
-                    for (int r = 0; r < R; ++r) W[r] = Wi[r] = (real_t)0;
-                    for (int t = tb; t < tb + nt; ++t) {
-                        const rec_t rec = s_rec[t];
-                        // sign of row r: parity of z over the lane / row-block bits XOR the register-row pattern
-                        const uint32_t m = (rec.zp >> 16) ^ (0u - (uint32_t)(__popc(rec.zp & jhi) & 1));
-#pragma unroll
-                        for (int r = 0; r < R; ++r) W[r] += flip_sign(rec.c, m << (31 - r));
-                        if constexpr (CPLX) {
-#pragma unroll
-                            for (int r = 0; r < R; ++r) Wi[r] += flip_sign(rec.ci, m << (31 - r));
-                        }
+                    switch ((d.y >> RNG_KIND_SHIFT) & 3u) {
+                        QFE_RANGE(KIND_FAST)
+                        QFE_RANGE(KIND_SINGLE)
+                        QFE_RANGE(KIND_MULTI)
+                        QFE_RANGE(KIND_GENERIC)
+                        default: break;
                     }
                 }
-                tb += nt;
-                const cplx_t* pblk = tile + (blk ^ (xl >> RB)) * BLK_STRIDE;
-                double g_re = 0.0, g_im = 0.0;
-                double& o_re = (MODE == MODE_BATCH) ? g_re : e_re;
-                double& o_im = (MODE == MODE_BATCH) ? g_im : e_im;
-                switch (xl & (R - 1)) {
-                    case 0: group_rows<real_t, CPLX, MODE, 0>(pblk, W, Wi, imag, half, own, acc_re, acc_im, o_re, o_im, e_half); break;
-                    case 1: group_rows<real_t, CPLX, MODE, 1>(pblk, W, Wi, imag, half, own, acc_re, acc_im, o_re, o_im, e_half); break;
-                    case 2: group_rows<real_t, CPLX, MODE, 2>(pblk, W, Wi, imag, half, own, acc_re, acc_im, o_re, o_im, e_half); break;
-                    case 3: group_rows<real_t, CPLX, MODE, 3>(pblk, W, Wi, imag, half, own, acc_re, acc_im, o_re, o_im, e_half); break;
-                    case 4: group_rows<real_t, CPLX, MODE, 4>(pblk, W, Wi, imag, half, own, acc_re, acc_im, o_re, o_im, e_half); break;
-                    case 5: group_rows<real_t, CPLX, MODE, 5>(pblk, W, Wi, imag, half, own, acc_re, acc_im, o_re, o_im, e_half); break;
-                    case 6: group_rows<real_t, CPLX, MODE, 6>(pblk, W, Wi, imag, half, own, acc_re, acc_im, o_re, o_im, e_half); break;
-                    default: group_rows<real_t, CPLX, MODE, 7>(pblk, W, Wi, imag, half, own, acc_re, acc_im, o_re, o_im, e_half); break;
-                }
-                if (MODE == MODE_BATCH) {
-#pragma unroll
-                    for (int d = 16; d > 0; d >>= 1) {
-                        g_re += __shfl_down_sync(0xffffffffu, g_re, d);
-                        g_im += __shfl_down_sync(0xffffffffu, g_im, d);
-                    }
-                    if (lane == 0) {  // only this warp writes its own row of s_acc: deterministic
-                        double2 cur = s_acc[warp * nG + g];
-                        cur.x += g_re;
-                        cur.y += g_im;
-                        s_acc[warp * nG + g] = cur;
-                    }
-                }
+#undef QFE_RANGE
             }
             if (MODE == MODE_EXPECT || MODE == MODE_APPLY) {
 #pragma unroll
@@ -388,7 +509,7 @@ __global__ void __launch_bounds__(NT, 1) tile_sweep_kernel(const __grid_constant
                     const uint32_t j = jhi | (uint32_t)r;
                     const uint64_t gidx = base | (j & lowmask) | s_spread[(j >> low) & 63] | s_spread[64 + ((j >> (low + 6)) & 63)];
                     if (MODE == MODE_EXPECT) {
-                        const cplx_t b = a.same_tile ? tile[blk * BLK_STRIDE + r] : bra[gidx];
+                        const cplx_t b = a.same_tile ? tile[w0 ^ (uint32_t)r] : bra[gidx];
                         e_re += (double)b.x * (double)acc_re[r] + (double)b.y * (double)acc_im[r];
                         e_im += (double)b.x * (double)acc_im[r] - (double)b.y * (double)acc_re[r];
                     } else {
@@ -528,7 +649,7 @@ struct qfe_plan {
     bool batch = false;
     bool force_direct = false;
     int device = 0;
-    DevBuf g_hdr, t_zl, t_zo, t_cre, t_cim, d_x, d_z, d_cre, d_cim, dg_begin;
+    DevBuf g_hdr, r_desc, t_zl, t_zo, t_cre, t_cim, d_x, d_z, d_cre, d_cim, dg_begin;
 };
 
 namespace qfe {
@@ -550,7 +671,7 @@ static size_t sweep_smem_bytes(const SweepHost& sw, int n_terms, int n_groups, i
     const size_t cplx_bytes = dtype == QFE_C128 ? 16 : 8;
     const size_t rec_bytes = dtype == QFE_C128 ? (sw.complex_w ? sizeof(TermRec<double, true>) : sizeof(TermRec<double, false>))
                                                : (sw.complex_w ? sizeof(TermRec<float, true>) : sizeof(TermRec<float, false>));
-    return smem_layout(sw.k, n_terms, n_groups, cplx_bytes, rec_bytes, batch).total;
+    return smem_layout(sw.k, n_terms, n_groups, sw.range_end - sw.range_begin, cplx_bytes, rec_bytes, batch).total;
 }
 
 template <typename real_t, bool CPLX, int MODE>
@@ -586,6 +707,8 @@ static int launch_direct(qfe_ctx* ctx, const DirectArgs& args, dim3 grid, int dt
 
 static void fill_sweep_args(const qfe_plan* p, const SweepHost& s, SweepArgs& a) {
     a.g_hdr = p->g_hdr.as<uint32_t>() + 2 * (size_t)s.group_begin;
+    a.r_desc = p->r_desc.as<uint32_t>() + 2 * (size_t)s.range_begin;
+    a.n_ranges = s.range_end - s.range_begin;
     a.t_zl = p->t_zl.as<uint32_t>() + s.term_begin;
     a.t_zo = p->t_zo.as<uint64_t>() + s.term_begin;
     a.t_cre = p->t_cre.as<double>() + s.term_begin;
@@ -740,7 +863,7 @@ int qfe_plan_create(qfe_ctx* ctx, const qfe_terms* t, int n_local, int shard, in
     }
     cudaStream_t s = ctx->stream;
     int rc = QFE_OK;
-    if ((rc = upload(p->g_hdr, p->h.g_hdr, s)) || (rc = upload(p->t_zl, p->h.t_zl, s)) || (rc = upload(p->t_zo, p->h.t_zo, s)) ||
+    if ((rc = upload(p->g_hdr, p->h.g_hdr, s)) || (rc = upload(p->r_desc, p->h.r_desc, s)) || (rc = upload(p->t_zl, p->h.t_zl, s)) || (rc = upload(p->t_zo, p->h.t_zo, s)) ||
         (rc = upload(p->t_cre, p->h.t_cre, s)) || (rc = upload(p->t_cim, p->h.t_cim, s)) || (rc = upload(p->d_x, p->h.d_x, s)) ||
         (rc = upload(p->d_z, p->h.d_z, s)) || (rc = upload(p->d_cre, p->h.d_cre, s)) || (rc = upload(p->d_cim, p->h.d_cim, s)) ||
         (rc = upload(p->dg_begin, p->h.dg_begin, s))) {

@@ -69,47 +69,71 @@ extern "C" int plan_emul_run(int n, int64_t T, const uint64_t* x, const uint64_t
                         seen[base | pos] = 1;
                     }
                 }
-                // <psi|G|psi> with bra == ket on the same tile may visit half the rows of a Hermitian group (HDR_HALF)
+                // <psi|G|psi> with bra == ket on the same tile may visit half the rows of a Hermitian range (skip bit)
                 const bool same = (bra == ket) && s.ket_xor == 0 && half_visit;
                 for (uint32_t j = 0; j < tile_amps; ++j) {
                     const uint64_t row = base | tile_spread(s, j);
-                    int64_t tb = s.term_begin;
                     cplx acc_row(0.0, 0.0);
-                    for (int g = s.group_begin; g < s.group_end; ++g) {
-                        const uint32_t ha = p.g_hdr[2 * g], hb = p.g_hdr[2 * g + 1];
-                        const uint32_t xl = ha & HDR_XL_MASK;
-                        const int nt = (int)((ha >> HDR_NT_SHIFT) & HDR_NT_MASK);
-                        const bool imag = ha & HDR_IMAG;
-                        const uint32_t skip = hb & HDR_SKIP_MASK;
-                        if (((ha & HDR_HALF) != 0) != (skip != 0)) return 10;
-                        if (skip && (skip != (1u << (31 - __builtin_clz(xl))) || skip < (1u << PLAN_U_SHIFT))) return 11;  // highest X bit, warp-uniform
-                        cplx w(0.0, 0.0);
-                        uint32_t zreg0 = 0;
-                        bool single = true;
-                        for (int64_t tt = tb; tt < tb + nt; ++tt) {
-                            const uint32_t zl = p.t_zl[tt] & 0xffffu, pat = (p.t_zl[tt] >> 16) & 0xffu;
-                            if (zl & 7u) return 12;  // register bits live in the pattern only
-                            const uint32_t jr = j & 7u;
-                            const int par = (__builtin_popcount(zl & j) + (int)((pat >> jr) & 1u) + __builtin_popcountll(p.t_zo[tt] & base)) & 1;
-                            if (tt == tb)
-                                zreg0 = pat;
-                            else if (pat != zreg0)
-                                single = false;
-                            cplx cc = imag ? cplx(0.0, p.t_cre[tt]) : cplx(p.t_cre[tt], p.t_cim[tt]);
-                            w += par ? -cc : cc;
+                    int g_expect = 0;
+                    int64_t t_expect = 0;
+                    for (int ri = s.range_begin; ri < s.range_end; ++ri) {
+                        const uint32_t d0 = p.r_desc[2 * ri], d1 = p.r_desc[2 * ri + 1];
+                        const int g0 = (int)(d0 & 0xffffu), g1 = (int)(d0 >> 16);
+                        const int kind = (int)((d1 >> RNG_KIND_SHIFT) & 3u);
+                        const uint32_t skipbit = d1 >> RNG_SKIP_SHIFT;
+                        if (g0 != g_expect || (int64_t)(d1 & 0xffffu) != t_expect || g1 <= g0) return 10;  // ranges tile the sweep's groups in order
+                        if (skipbit && (skipbit < (uint32_t)PLAN_U_SHIFT || skipbit >= (uint32_t)s.k || s.ket_xor != 0)) return 11;
+                        int64_t tb = s.term_begin + t_expect;
+                        for (int gl = g0; gl < g1; ++gl) {
+                            const int g = s.group_begin + gl;
+                            const uint32_t ha = p.g_hdr[2 * g], hb = p.g_hdr[2 * g + 1];
+                            const uint32_t xl = tile_word_of(ha & HDR_XL_MASK);  // the header keeps the X mask in word form (an involution)
+                            const int nt = (int)((ha >> HDR_NT_SHIFT) & HDR_NT_MASK);
+                            const bool imag = ha & HDR_IMAG;
+                            if (skipbit && (31 - __builtin_clz(xl)) != (int)skipbit) return 13;  // the skip bit is the top X bit
+                            cplx w(0.0, 0.0);
+                            int counts[8] = {0};
+                            uint32_t prev_pat = 0;
+                            for (int64_t tt = tb; tt < tb + nt; ++tt) {
+                                const uint32_t zl = p.t_zl[tt] & 0xffffu, pat = (p.t_zl[tt] >> 16) & 0xffu;
+                                if (zl & 7u) return 14;  // register bits live in the pattern only
+                                // pattern -> z bits on the register rows: bit i of zreg = pattern bit (1 << i)
+                                const uint32_t zreg = ((pat >> 1) & 1u) | (((pat >> 2) & 1u) << 1) | (((pat >> 4) & 1u) << 2);
+                                counts[zreg]++;
+                                if (kind == KIND_FAST && zreg != 0) return 15;
+                                if (kind == KIND_SINGLE && (pat != ((hb >> HDR_PAT_SHIFT) & 0xffu) || zreg == 0)) return 16;
+                                if (kind == KIND_MULTI && tt > tb && pat != prev_pat && zreg < (uint32_t)0) return 17;
+                                prev_pat = pat;
+                                const int par = (__builtin_popcount(zl & j) + (int)((pat >> (j & 7u)) & 1u) + __builtin_popcountll(p.t_zo[tt] & base)) & 1;
+                                cplx cc = imag ? cplx(0.0, p.t_cre[tt]) : cplx(p.t_cre[tt], p.t_cim[tt]);
+                                w += par ? -cc : cc;
+                            }
+                            if (kind == KIND_MULTI) {
+                                // sorted by zreg with the advertised 4-bit counts
+                                uint32_t last = 0;
+                                for (int64_t tt = tb; tt < tb + nt; ++tt) {
+                                    const uint32_t pat = (p.t_zl[tt] >> 16) & 0xffu;
+                                    const uint32_t zreg = ((pat >> 1) & 1u) | (((pat >> 2) & 1u) << 1) | (((pat >> 4) & 1u) << 2);
+                                    if (zreg < last) return 17;
+                                    last = zreg;
+                                }
+                                for (int v = 0; v < 8; ++v)
+                                    if ((int)((hb >> (4 * v)) & 15u) != counts[v]) return 18;
+                            }
+                            if ((kind != KIND_GENERIC) && s.complex_w) return 19;
+                            tb += nt;
+                            const cplx contrib = w * tile[j ^ xl];
+                            acc_row += contrib;
+                            if (same && skipbit) {
+                                if (!((j >> skipbit) & 1u)) out[p.g_slot[g]] += 2.0 * std::real(std::conj(bra[row]) * contrib);
+                            } else {
+                                out[p.g_slot[g]] += std::conj(bra[row]) * contrib;
+                            }
                         }
-                        if (single != ((ha & HDR_SINGLE) != 0)) return 13;
-                        if (single && ((hb >> HDR_PAT_SHIFT) & 0xffu) != zreg0) return 14;
-                        tb += nt;
-                        const cplx contrib = w * tile[j ^ xl];
-                        acc_row += contrib;
-                        if (same && skip) {
-                            if (!(j & skip)) out[p.g_slot[g]] += 2.0 * std::real(std::conj(bra[row]) * contrib);
-                        } else {
-                            out[p.g_slot[g]] += std::conj(bra[row]) * contrib;
-                        }
+                        g_expect = g1;
+                        t_expect = tb - s.term_begin;
                     }
-                    if (tb != s.term_end) return 8;
+                    if (g_expect != s.group_end - s.group_begin || s.term_begin + t_expect != s.term_end) return 8;
                     y[row] += acc_row;
                 }
             }
