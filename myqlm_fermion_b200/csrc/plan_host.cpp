@@ -262,9 +262,10 @@ int build_plan(const TermView& t, int n_local, int shard, const PlanLimits& lim,
                 int64_t nterms = 0;
                 for (size_t g = 0; g < ng; ++g) {
                     if (done[g] || ((need[g] & ~L) != kxor)) continue;
-                    if ((int)take.size() >= lim.max_groups || nterms + groups[g].nt > lim.max_terms) break;
+                    const int nt_padded = (groups[g].nt + 1) & ~1;  // staged term lists are padded to an even length
+                    if ((int)take.size() >= lim.max_groups || nterms + nt_padded > lim.max_terms) break;
                     take.push_back(g);
-                    nterms += groups[g].nt;
+                    nterms += nt_padded;
                 }
                 // classify coefficients
                 bool cplx = false;
@@ -331,12 +332,11 @@ int build_plan(const TermView& t, int n_local, int shard, const PlanLimits& lim,
                         for (uint32_t r = 0; r <= regmask; ++r) pat0 |= (uint32_t)(popc64(zreg0 & r) & 1) << r;
                         gi.word_b = pat0 << HDR_PAT_SHIFT;
                     } else {
-                        bool small = true;
-                        for (int v = 0; v <= (int)regmask; ++v)
-                            if (counts[v] > 15) small = false;
-                        if (small) {
+                        // few distinct register-row z patterns relative to the term count: per-pattern sums pay off
+                        int n_classes = 0;
+                        for (int v = 0; v <= (int)regmask; ++v) n_classes += counts[v] > 0;
+                        if (g.nt >= 2 * n_classes) {
                             gi.kind = KIND_MULTI;
-                            for (int v = 0; v <= (int)regmask; ++v) gi.word_b |= (uint32_t)counts[v] << (4 * v);
                             std::stable_sort(gi.order.begin(), gi.order.end(), [&](int64_t p, int64_t q) {
                                 return (compress_to_tile(s, (recs[p].z & lomask) & L) & regmask) < (compress_to_tile(s, (recs[q].z & lomask) & L) & regmask);
                             });
@@ -374,7 +374,14 @@ int build_plan(const TermView& t, int n_local, int shard, const PlanLimits& lim,
                         out.t_cre.push_back(gi.imag ? recs[i].im : recs[i].re);
                         out.t_cim.push_back(gi.imag ? 0.0 : recs[i].im);
                     }
-                    out.g_hdr.push_back(tile_word_of(gi.xl) | ((uint32_t)g.nt << HDR_NT_SHIFT) | (gi.imag ? HDR_IMAG : 0u));
+                    const int nt_emit = (g.nt + 1) & ~1;
+                    if (nt_emit != g.nt) {  // zero-coefficient copy of the last term: keeps the list even (and its pattern run intact)
+                        out.t_zl.push_back(out.t_zl.back());
+                        out.t_zo.push_back(out.t_zo.back());
+                        out.t_cre.push_back(0.0);
+                        out.t_cim.push_back(0.0);
+                    }
+                    out.g_hdr.push_back(tile_word_of(gi.xl) | ((uint32_t)nt_emit << HDR_NT_SHIFT) | (gi.imag ? HDR_IMAG : 0u));
                     out.g_hdr.push_back(gi.word_b);
                     out.g_slot.push_back(g.slot);
                     done[gi.gi] = 1;

@@ -39,8 +39,7 @@ constexpr uint32_t HDR_XL_MASK = 0x1fffu;   // bits 0..12: tile-local X mask in 
 constexpr int HDR_NT_SHIFT = 13;            // bits 13..24: number of terms (<= 4095)
 constexpr uint32_t HDR_NT_MASK = 0xfffu;
 constexpr uint32_t HDR_IMAG = 1u << 25;     // gather coefficients purely imaginary (stored in t_cre)
-// group header word b: KIND_SINGLE: bits 16..23 = register-row sign pattern of the group;
-//                      KIND_MULTI: eight 4-bit term counts, one per value of the z bits on the register rows (terms sorted by it)
+// group header word b: KIND_SINGLE: bits 16..23 = register-row sign pattern of the group
 constexpr int HDR_PAT_SHIFT = 16;
 
 // A sweep's groups are ordered into *ranges* of equal (skip bit, kind):
@@ -49,7 +48,7 @@ constexpr int HDR_PAT_SHIFT = 16;
 //   kind:     how W(row) = sum_t c_t (-1)^{|z_t & row|} is formed for the thread's 8 register rows;
 enum { KIND_FAST = 0,     // no z bit on the register rows: W is the same for the 8 rows
        KIND_SINGLE = 1,   // all terms share their z bits on the register rows: W = +-S by a group pattern
-       KIND_MULTI = 2,    // terms sorted by their register-row z bits (<= 15 per value): class sums, then an 8-point Walsh-Hadamard
+       KIND_MULTI = 2,    // terms sorted by their register-row z bits: one signed sum per run, folded in with the run's pattern
        KIND_GENERIC = 3   // one signed add per (term, row); the only kind of complex-coefficient sweeps
 };
 // range descriptor: word 0 = first group | (one past the last group) << 16 (sweep-local);

@@ -73,30 +73,20 @@ struct SweepArgs {
     uint64_t spread[128];
 };
 
-struct SmemLayout {
-    size_t rec, hdr, rng, spread, acc, red, total;
-};
-
-__host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~size_t(15); }
-
-__host__ __device__ inline SmemLayout smem_layout(int k, int n_terms, int n_groups, int n_ranges, size_t cplx_bytes, size_t rec_bytes, bool batch) {
-    SmemLayout L;
-    size_t off = align16((size_t(1) << k) * cplx_bytes);
-    L.rec = off;
-    off += align16((size_t)n_terms * rec_bytes);
-    L.hdr = off;
-    off += align16((size_t)n_groups * 8);
-    L.rng = off;
-    off += align16((size_t)n_ranges * 8);
-    L.spread = off;
-    off += 128 * 8;
-    L.acc = off;
-    if (batch) off += (size_t)NW * n_groups * sizeof(double2);
-    L.red = off;
-    off += NW * sizeof(double2);
-    L.total = off;
-    return L;
-}
+// Fixed shared-memory map (bytes), sized for the largest sweep (2^13 complex128 amplitudes, 2048 complex-coefficient terms):
+// constant offsets let every access be [register + immediate] with nothing to recompute inside the group loop.
+constexpr uint32_t SM_TILE = 0;                         // 128 KB tile
+constexpr uint32_t SM_REC = 131072;                     // 64 KB staged terms (2048 x 32 B)
+constexpr uint32_t SM_ACC = SM_REC + 32768;             // BATCH only (<= 1024 terms staged): per-warp per-group accumulators, 32 KB
+constexpr uint32_t SM_HDR = SM_REC + 65536;             // 4 KB group headers (512 x 8 B)
+constexpr uint32_t SM_RNG = SM_HDR + 4096;              // 2 KB range descriptors (256 x 8 B)
+constexpr uint32_t SM_SPREAD = SM_RNG + 2048;           // 1 KB tile-index -> shard-position tables
+constexpr uint32_t SM_RED = SM_SPREAD + 1024;           // block reduction scratch
+constexpr uint32_t SM_TOTAL = SM_RED + NW * 16;
+constexpr int SWEEP_MAX_TERMS = 2048, SWEEP_MAX_GROUPS = 512;  // ranges per sweep <= 6 skip bits x 4 kinds
+constexpr int BATCH_MAX_TERMS = 1024, BATCH_MAX_GROUPS = 128;
+static_assert((size_t)NW * BATCH_MAX_GROUPS * 16 <= 32768 && BATCH_MAX_TERMS * 32 <= 32768, "batch accumulators share the term area");
+static_assert(SM_TOTAL <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
 
 __device__ __forceinline__ double2 block_reduce_sum(double2 v, double2* s_red) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -154,30 +144,20 @@ __device__ __forceinline__ void load_rec(const TermRec<float, true>* p, float& c
 
 __device__ __forceinline__ uint32_t tile_word(uint32_t j) { return j ^ ((j >> RB) & (R - 1)); }
 
-// S = sum_t c_t (-1)^{|z_t & jhi|} over terms [t, t + nt): four independent loads, two independent sums
+// S = sum_t c_t (-1)^{|z_t & jhi|} over terms [t, t + nt); nt is even (the planner pads with a zero term): two independent
+// loads and sums per step
 template <typename rec_t, typename real_t>
 __device__ __forceinline__ real_t signed_sum(const rec_t* __restrict__ s_rec, int t, const int nt, const uint32_t jhi) {
     real_t S0 = (real_t)0, S1 = (real_t)0;
     const int te = t + nt;
-    for (; t + 4 <= te; t += 4) {
-        real_t c0, c1, c2, c3;
-        uint32_t z0, z1, z2, z3;
+#pragma unroll 1
+    for (; t < te; t += 2) {
+        real_t c0, c1;
+        uint32_t z0, z1;
         load_rec(s_rec + t, c0, z0);
         load_rec(s_rec + t + 1, c1, z1);
-        load_rec(s_rec + t + 2, c2, z2);
-        load_rec(s_rec + t + 3, c3, z3);
-        c0 = flip_sign(c0, (uint32_t)__popc(z0 & jhi) << 31);
-        c1 = flip_sign(c1, (uint32_t)__popc(z1 & jhi) << 31);
-        c2 = flip_sign(c2, (uint32_t)__popc(z2 & jhi) << 31);
-        c3 = flip_sign(c3, (uint32_t)__popc(z3 & jhi) << 31);
-        S0 += c0 + c2;
-        S1 += c1 + c3;
-    }
-    for (; t < te; ++t) {
-        real_t c;
-        uint32_t z;
-        load_rec(s_rec + t, c, z);
-        S1 += flip_sign(c, (uint32_t)__popc(z & jhi) << 31);
+        S0 += flip_sign(c0, (uint32_t)__popc(z0 & jhi) << 31);
+        S1 += flip_sign(c1, (uint32_t)__popc(z1 & jhi) << 31);
     }
     return S0 + S1;
 }
@@ -192,14 +172,19 @@ __device__ __forceinline__ void group_rows(const typename CplxOf<real_t>::type* 
     if (MODE == MODE_EXPECT_SAME && half) {
         // Hermitian group: the pair (b, b^x) sums to 2 Re(conj(psi_b) W psi_p); only rows with the skip bit clear get here.
         // real W: W (a a' + b b');  imaginary W = i w: -w Im(conj(psi_b) psi_p) = w (b a' - a b')
-        real_t s0 = (real_t)0, s1 = (real_t)0;  // two chains keep the FP64 pipe busy
+        real_t s0 = (real_t)0, s1 = (real_t)0, s2 = (real_t)0, s3 = (real_t)0;  // independent chains keep the FP64 pipe busy
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const cplx_t p = tile[pw ^ (uint32_t)r];
             const real_t u = imag ? p.y : p.x, v = imag ? p.x : p.y;
             if (UNIFORM) {
-                s0 = fma(imag ? -own[r].x : own[r].x, u, s0);
-                s1 = fma(own[r].y, v, s1);
+                if (r & 1) {
+                    s2 = fma(imag ? -own[r].x : own[r].x, u, s2);
+                    s3 = fma(own[r].y, v, s3);
+                } else {
+                    s0 = fma(imag ? -own[r].x : own[r].x, u, s0);
+                    s1 = fma(own[r].y, v, s1);
+                }
             } else {
                 const real_t t = (imag ? -own[r].x : own[r].x) * u + own[r].y * v;
                 if (r & 1)
@@ -208,7 +193,7 @@ __device__ __forceinline__ void group_rows(const typename CplxOf<real_t>::type* 
                     s0 = fma(W[r], t, s0);
             }
         }
-        e_half += UNIFORM ? (double)(W[0] * (s0 + s1)) : (double)(s0 + s1);
+        e_half += UNIFORM ? (double)(W[0] * ((s0 + s1) + (s2 + s3))) : (double)(s0 + s1);
     } else if (MODE == MODE_EXPECT_SAME || (MODE == MODE_BATCH && UNIFORM)) {
         // full complex value of sum_r conj(own_r) Wc p_r  (own = ket rows for EXPECT_SAME, bra rows for BATCH)
         real_t sr = (real_t)0, si = (real_t)0, sr2 = (real_t)0, si2 = (real_t)0;
@@ -309,31 +294,27 @@ __device__ __forceinline__ void process_range(const typename CplxOf<real_t>::typ
 #pragma unroll
             for (int r = 0; r < R; ++r) W[r] = flip_sign(S, pat << (31 - r));
         } else if (KIND == KIND_MULTI) {
-            // class sums over the terms sharing their register-row z bits, then W = H_8 S (in-place butterflies)
-            int t = tb;
+            // terms sorted by their register-row z bits: one signed sum per run of equal bits, folded into the 8 rows with the
+            // run's sign pattern (kept in bits 16..23 of the term word)
 #pragma unroll
-            for (int v = 0; v < R; ++v) {
-                const int nv = (int)((hdr.y >> (4 * v)) & 15u);
-                real_t S = (real_t)0;
-                for (int i = 0; i < nv; ++i, ++t) {
-                    real_t c;
-                    uint32_t z;
-                    load_rec(s_rec + t, c, z);
-                    S += flip_sign(c, (uint32_t)__popc(z & jhi) << 31);
+            for (int r = 0; r < R; ++r) W[r] = (real_t)0;
+            real_t S = (real_t)0;
+            uint32_t cur = s_rec[tb].zp >> 16;
+#pragma unroll 1
+            for (int t = tb; t < tb + nt; ++t) {
+                real_t c;
+                uint32_t z;
+                load_rec(s_rec + t, c, z);
+                if ((z >> 16) != cur) {  // warp-uniform
+#pragma unroll
+                    for (int r = 0; r < R; ++r) W[r] += flip_sign(S, cur << (31 - r));
+                    S = (real_t)0;
+                    cur = z >> 16;
                 }
-                W[v] = S;
+                S += flip_sign(c, (uint32_t)__popc(z & jhi) << 31);
             }
 #pragma unroll
-            for (int bit = 1; bit < R; bit <<= 1) {
-#pragma unroll
-                for (int v = 0; v < R; ++v) {
-                    if (!(v & bit)) {
-                        const real_t a = W[v], b = W[v | bit];
-                        W[v] = a + b;
-                        W[v | bit] = a - b;
-                    }
-                }
-            }
+            for (int r = 0; r < R; ++r) W[r] += flip_sign(S, cur << (31 - r));
         } else {
 #pragma unroll
             for (int r = 0; r < R; ++r) W[r] = (real_t)0;
@@ -378,14 +359,13 @@ __global__ void __launch_bounds__(NT, 1) tile_sweep_kernel(const __grid_constant
     const int k = a.k;
     const uint32_t tile_amps = 1u << k;
     const int nT = a.n_terms, nG = a.n_groups, nR = a.n_ranges;
-    const SmemLayout L = smem_layout(k, nT, nG, nR, sizeof(cplx_t), sizeof(rec_t), MODE == MODE_BATCH);
-    cplx_t* tile = reinterpret_cast<cplx_t*>(smem);
-    rec_t* s_rec = reinterpret_cast<rec_t*>(smem + L.rec);
-    uint2* s_hdr = reinterpret_cast<uint2*>(smem + L.hdr);
-    uint2* s_rng = reinterpret_cast<uint2*>(smem + L.rng);
-    uint64_t* s_spread = reinterpret_cast<uint64_t*>(smem + L.spread);
-    double2* s_acc = reinterpret_cast<double2*>(smem + L.acc);
-    double2* s_red = reinterpret_cast<double2*>(smem + L.red);
+    cplx_t* tile = reinterpret_cast<cplx_t*>(smem + SM_TILE);
+    rec_t* s_rec = reinterpret_cast<rec_t*>(smem + SM_REC);
+    uint2* s_hdr = reinterpret_cast<uint2*>(smem + SM_HDR);
+    uint2* s_rng = reinterpret_cast<uint2*>(smem + SM_RNG);
+    uint64_t* s_spread = reinterpret_cast<uint64_t*>(smem + SM_SPREAD);
+    double2* s_acc = reinterpret_cast<double2*>(smem + SM_ACC);
+    double2* s_red = reinterpret_cast<double2*>(smem + SM_RED);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const cplx_t* __restrict__ ket = reinterpret_cast<const cplx_t*>(a.ket);
@@ -667,12 +647,7 @@ static int find_class(const qfe_plan* p, int x_hi) {
     return -1;
 }
 
-static size_t sweep_smem_bytes(const SweepHost& sw, int n_terms, int n_groups, int dtype, bool batch) {
-    const size_t cplx_bytes = dtype == QFE_C128 ? 16 : 8;
-    const size_t rec_bytes = dtype == QFE_C128 ? (sw.complex_w ? sizeof(TermRec<double, true>) : sizeof(TermRec<double, false>))
-                                               : (sw.complex_w ? sizeof(TermRec<float, true>) : sizeof(TermRec<float, false>));
-    return smem_layout(sw.k, n_terms, n_groups, sw.range_end - sw.range_begin, cplx_bytes, rec_bytes, batch).total;
-}
+static size_t sweep_smem_bytes(const SweepHost&, int, int, int, bool) { return SM_TOTAL; }
 
 template <typename real_t, bool CPLX, int MODE>
 static int launch_tile(qfe_ctx* ctx, const SweepArgs& args, int grid, size_t smem) {
@@ -839,11 +814,11 @@ int qfe_plan_create(qfe_ctx* ctx, const qfe_terms* t, int n_local, int shard, in
     lim.tile_bits = tile_bits > 0 ? tile_bits : 13;
     if (lim.tile_bits > 13) lim.tile_bits = 13;  // 2^13 complex128 amplitudes = 128 KB of the 227 KB shared memory
     if (p->batch) {
-        lim.max_terms = 1024;
-        lim.max_groups = 128;
+        lim.max_terms = BATCH_MAX_TERMS;
+        lim.max_groups = BATCH_MAX_GROUPS;
     } else {
-        lim.max_terms = 2048;
-        lim.max_groups = 512;
+        lim.max_terms = SWEEP_MAX_TERMS;
+        lim.max_groups = SWEEP_MAX_GROUPS;
     }
     p->lim = lim;
     TermView v;

@@ -43,7 +43,7 @@ extern "C" int plan_emul_run(int n, int64_t T, const uint64_t* x, const uint64_t
     // every group of every class must be covered by exactly one sweep
     {
         size_t ng_tiled = p.g_hdr.size() / 2, ng_direct = p.dg_slot.size();
-        if (ng_tiled != ng_direct || p.t_zl.size() != p.d_x.size()) return 3;
+        if (ng_tiled != ng_direct || p.t_zl.size() < p.d_x.size() || p.t_zl.size() > p.d_x.size() + ng_direct) return 3;  // + even-length padding
     }
     for (const ClassHost& cls : p.classes) {
         if (cls.x_hi != x_hi) continue;
@@ -117,10 +117,9 @@ extern "C" int plan_emul_run(int n, int64_t T, const uint64_t* x, const uint64_t
                                     if (zreg < last) return 17;
                                     last = zreg;
                                 }
-                                for (int v = 0; v < 8; ++v)
-                                    if ((int)((hb >> (4 * v)) & 15u) != counts[v]) return 18;
                             }
                             if ((kind != KIND_GENERIC) && s.complex_w) return 19;
+                            if (nt & 1) return 20;  // staged term lists are padded to an even length
                             tb += nt;
                             const cplx contrib = w * tile[j ^ xl];
                             acc_row += contrib;
