@@ -59,3 +59,38 @@ def hubbard_chain_t(ns: int, t: float = -1.0) -> np.ndarray:
     for i in range(ns - 1):
         t_mat[i, i + 1] = t_mat[i + 1, i] = t
     return t_mat
+
+
+def uccsd_excitations(n_electrons: int, nqbits: int):
+    """(a, i) and (b, a, j, i) spin-orbital index tuples of the UCCSD pool in the reference's order
+    (/root/reference/qat/fermion/chemistry/ucc.py:554-580, 691-713): occupied = the first n_electrons
+    spin-orbitals, spin-preserving singles, spin-matching doubles, each list sorted descending, singles first."""
+    if nqbits % 2 or n_electrons % 2:
+        raise ValueError("Only even values of nqbits / n_electrons are allowed.")
+    occ = list(range(n_electrons))
+    unocc = list(range(n_electrons, nqbits))
+    singles = []
+    for a in unocc[::2]:
+        for i in occ[::2]:
+            singles.append((a, i))
+            singles.append((a + 1, i + 1))
+    doubles = []
+    for ia, a in enumerate(unocc):
+        for b in unocc[ia + 1 :]:
+            for ii, i in enumerate(occ):
+                for j in occ[ii + 1 :]:
+                    if (a % 2 == i % 2 and b % 2 == j % 2) or (a % 2 == j % 2 and b % 2 == i % 2):
+                        doubles.append((b, a, j, i))
+    return sorted(singles)[::-1] + sorted(doubles)[::-1]
+
+
+def uccsd_pool_fermion_terms(n_electrons: int, nqbits: int):
+    """Hermitian generators i(T - T^dagger) as fermionic term lists (ucc.py:232-288): one list per excitation."""
+    pool = []
+    for ex in uccsd_excitations(n_electrons, nqbits):
+        if len(ex) == 2:
+            op, idx, conj = "Cc", list(ex), [ex[1], ex[0]]
+        else:
+            op, idx, conj = "CCcc", list(ex), [ex[2], ex[3], ex[0], ex[1]]
+        pool.append([(1j, op, idx), (-1j, op, conj)])
+    return pool
