@@ -5,6 +5,7 @@
 // linked into libqfe.so.
 #include <complex>
 #include <cstdint>
+#include <cstdio>
 #include <cstring>
 #include <vector>
 
@@ -169,5 +170,42 @@ extern "C" int plan_emul_stats(int n, int64_t T, const uint64_t* x, const uint64
     stats[2] = (int64_t)p.t_zl.size();
     stats[3] = (int64_t)p.classes.size();
     for (size_t i = 0; i < p.sweeps.size() && (int32_t)i < capacity; ++i) groups_per_sweep[i] = p.sweeps[i].group_end - p.sweeps[i].group_begin;
+    return 0;
+}
+
+// per-group dump of a plan (development aid for tools/plan_stats.py): one CSV line per group
+extern "C" int plan_emul_dump(int n, int64_t T, const uint64_t* x, const uint64_t* z, const double* c, const int32_t* owner, int64_t n_slots,
+                              const double* constant, int n_local, int shard, int tile_bits, int max_terms, int max_groups, const char* path) {
+    TermView v;
+    v.n = n;
+    v.T = T;
+    v.x = x;
+    v.z = z;
+    v.c = c;
+    v.owner = owner;
+    v.n_slots = n_slots;
+    v.constant = constant;
+    PlanLimits lim;
+    lim.tile_bits = tile_bits;
+    lim.max_terms = max_terms;
+    lim.max_groups = max_groups;
+    PlanHost p;
+    const char* err = nullptr;
+    if (build_plan(v, n_local, shard, lim, p, &err) != 0) return 1;
+    FILE* f = fopen(path, "w");
+    if (!f) return 2;
+    fprintf(f, "sweep,range,kind,skipbit,group,nt,xword,imag,tile_mask\n");
+    for (size_t si = 0; si < p.sweeps.size(); ++si) {
+        const SweepHost& s = p.sweeps[si];
+        for (int r = s.range_begin; r < s.range_end; ++r) {
+            const uint32_t d0 = p.r_desc[2 * r], d1 = p.r_desc[2 * r + 1];
+            for (uint32_t g = (d0 & 0xffffu); g < (d0 >> 16); ++g) {
+                const uint32_t h = p.g_hdr[2 * (s.group_begin + g)];
+                fprintf(f, "%zu,%d,%u,%u,%u,%u,%u,%u,%llu\n", si, r - s.range_begin, (d1 >> RNG_KIND_SHIFT) & 3u, d1 >> RNG_SKIP_SHIFT, g,
+                        (h >> HDR_NT_SHIFT) & HDR_NT_MASK, h & HDR_XL_MASK, (h & HDR_IMAG) ? 1u : 0u, (unsigned long long)s.tile_mask);
+            }
+        }
+    }
+    fclose(f);
     return 0;
 }
