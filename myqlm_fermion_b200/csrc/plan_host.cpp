@@ -289,100 +289,83 @@ int build_plan(const TermView& t, int n_local, int shard, const PlanLimits& lim,
                 s.term_begin = (int64_t)out.t_zl.size();
                 s.range_begin = (int32_t)(out.r_desc.size() / 2);
                 const uint32_t regmask = (1u << PLAN_REG_BITS) - 1u;
-                // classify every group, then order the sweep's groups by (skip bit, kind, K) so that the kernel
+                // classify every group, then order the sweep's groups by (skip bit, polarity, kind) so that the kernel
                 // walks homogeneous ranges: whole ranges are skipped / dispatched, not single groups
                 struct GInfo {
                     size_t gi;
-                    uint32_t xl, word_b;
+                    uint32_t xl;
                     bool imag;
-                    int kind, K, skipbit;
+                    int kind, skipbit, pol;
                     std::vector<int64_t> order;  // term emit order
                 };
+                auto zreg_of = [&](int64_t i) { return compress_to_tile(s, (recs[i].z & lomask) & L) & regmask; };
                 std::vector<GInfo> info(take.size());
+                double pol_load[PLAN_MAX_TILE_BITS + 1][2] = {{0.0}};
                 for (size_t a = 0; a < take.size(); ++a) {
                     const Group& g = groups[take[a]];
                     GInfo& gi = info[a];
                     gi.gi = take[a];
                     gi.xl = compress_to_tile(s, g.x_lo);
                     gi.imag = !cplx && imag[a];
-                    gi.K = (int)(gi.xl & regmask);
-                    bool single = true, hermitian = true;
-                    uint32_t zreg0 = 0;
-                    int counts[1 << PLAN_REG_BITS] = {0};
+                    bool fast = true, hermitian = true;
                     for (int64_t i = g.tb; i < g.tb + g.nt; ++i) {
-                        const uint32_t zreg = compress_to_tile(s, (recs[i].z & lomask) & L) & regmask;
-                        if (i == g.tb)
-                            zreg0 = zreg;
-                        else if (zreg != zreg0)
-                            single = false;
-                        counts[zreg]++;
+                        if (zreg_of(i) != 0) fast = false;
                         if (!recs[i].herm) hermitian = false;
                     }
                     gi.skipbit = 0;
-                    if (hermitian && !cplx && kxor == 0 && (gi.xl >> PLAN_U_SHIFT) != 0) gi.skipbit = 31 - __builtin_clz(gi.xl);
-                    gi.word_b = 0;
-                    for (int64_t i = g.tb; i < g.tb + g.nt; ++i) gi.order.push_back(i);
-                    if (cplx) {
-                        gi.kind = KIND_GENERIC;
-                    } else if (single && zreg0 == 0) {
-                        gi.kind = KIND_FAST;
-                    } else if (single) {
-                        gi.kind = KIND_SINGLE;
-                        uint32_t pat0 = 0;
-                        for (uint32_t r = 0; r <= regmask; ++r) pat0 |= (uint32_t)(popc64(zreg0 & r) & 1) << r;
-                        gi.word_b = pat0 << HDR_PAT_SHIFT;
-                    } else {
-                        // few distinct register-row z patterns relative to the term count: per-pattern sums pay off
-                        int n_classes = 0;
-                        for (int v = 0; v <= (int)regmask; ++v) n_classes += counts[v] > 0;
-                        if (g.nt >= 2 * n_classes) {
-                            gi.kind = KIND_MULTI;
-                            std::stable_sort(gi.order.begin(), gi.order.end(), [&](int64_t p, int64_t q) {
-                                return (compress_to_tile(s, (recs[p].z & lomask) & L) & regmask) < (compress_to_tile(s, (recs[q].z & lomask) & L) & regmask);
-                            });
-                        } else {
-                            gi.kind = KIND_GENERIC;
-                        }
+                    gi.pol = 0;
+                    if (hermitian && !cplx && !gi.imag && kxor == 0 && (gi.xl >> PLAN_SKIP_MIN_BIT) != 0) {
+                        gi.skipbit = 31 - __builtin_clz(gi.xl);
+                        // the rows with skip bit == pol do the work of this group: keep the two halves of every bit level
+                        const double cost = 48.0 + 6.0 * g.nt;
+                        gi.pol = pol_load[gi.skipbit][1] < pol_load[gi.skipbit][0] ? 1 : 0;
+                        pol_load[gi.skipbit][gi.pol] += cost;
                     }
+                    for (int64_t i = g.tb; i < g.tb + g.nt; ++i) gi.order.push_back(i);
+                    gi.kind = fast ? KIND_FAST : KIND_RUNS;
+                    if (!fast) std::stable_sort(gi.order.begin(), gi.order.end(), [&](int64_t p, int64_t q) { return zreg_of(p) < zreg_of(q); });
                 }
                 std::vector<size_t> ord(take.size());
                 for (size_t a = 0; a < ord.size(); ++a) ord[a] = a;
-                std::stable_sort(ord.begin(), ord.end(), [&](size_t p, size_t q) {
-                    const GInfo &A = info[p], &B = info[q];
-                    if (A.skipbit != B.skipbit) return A.skipbit < B.skipbit;
-                    return A.kind < B.kind;
-                });
+                auto range_key = [&](const GInfo& A) { return (A.skipbit << 3) | (A.pol << 2) | A.kind; };
+                std::stable_sort(ord.begin(), ord.end(), [&](size_t p, size_t q) { return range_key(info[p]) < range_key(info[q]); });
                 for (size_t oi = 0; oi < ord.size(); ++oi) {
                     const GInfo& gi = info[ord[oi]];
                     const Group& g = groups[gi.gi];
                     const uint32_t g_local = (uint32_t)(out.g_hdr.size() / 2 - s.group_begin);
                     const uint32_t t_local = (uint32_t)(out.t_zl.size() - s.term_begin);
-                    const bool new_range = oi == 0 || info[ord[oi - 1]].skipbit != gi.skipbit || info[ord[oi - 1]].kind != gi.kind;
+                    const bool new_range = oi == 0 || range_key(info[ord[oi - 1]]) != range_key(gi);
                     if (new_range) {
                         out.r_desc.push_back(g_local | ((g_local + 1) << 16));
-                        out.r_desc.push_back(t_local | ((uint32_t)gi.kind << RNG_KIND_SHIFT) | ((uint32_t)gi.skipbit << RNG_SKIP_SHIFT));
+                        out.r_desc.push_back(t_local | ((uint32_t)gi.kind << RNG_KIND_SHIFT) | ((uint32_t)gi.pol << RNG_POL_SHIFT) |
+                                             ((uint32_t)gi.skipbit << RNG_SKIP_SHIFT));
                     } else {
                         uint32_t& d0 = out.r_desc[out.r_desc.size() - 2];
                         d0 = (d0 & 0xffffu) | ((g_local + 1) << 16);
                     }
-                    for (int64_t i : gi.order) {
+                    size_t run_head = 0;
+                    for (size_t oi2 = 0; oi2 < gi.order.size(); ++oi2) {
+                        const int64_t i = gi.order[oi2];
                         const uint32_t zl = compress_to_tile(s, (recs[i].z & lomask) & L);
-                        uint32_t pat = 0;  // bit r = parity(z_reg & r)
-                        for (uint32_t r = 0; r <= regmask; ++r) pat |= (uint32_t)(popc64((zl & regmask) & r) & 1) << r;
-                        out.t_zl.push_back((zl & ~regmask) | (pat << 16));
+                        const uint32_t v = zl & regmask;
+                        if (oi2 == 0 || v != ((out.t_zl[run_head] >> TZ_V_SHIFT) & regmask)) run_head = out.t_zl.size();
+                        out.t_zl.push_back((zl & TZ_HI_MASK) | (v << TZ_V_SHIFT));
+                        out.t_zl[run_head] += 1u << TZ_RUN_SHIFT;
                         out.t_zo.push_back((recs[i].z & lomask) & ~L);
                         out.t_cre.push_back(gi.imag ? recs[i].im : recs[i].re);
                         out.t_cim.push_back(gi.imag ? 0.0 : recs[i].im);
                     }
-                    const int nt_emit = (g.nt + 1) & ~1;
-                    if (nt_emit != g.nt) {  // zero-coefficient copy of the last term: keeps the list even (and its pattern run intact)
-                        out.t_zl.push_back(out.t_zl.back());
+                    int nt_emit = g.nt;
+                    if (gi.kind == KIND_FAST && (g.nt & 1)) {  // zero-coefficient copy of the last term: keeps the list even
+                        out.t_zl.push_back(out.t_zl.back() & ~(0xfffu << TZ_RUN_SHIFT));
+                        out.t_zl[run_head] += 1u << TZ_RUN_SHIFT;
                         out.t_zo.push_back(out.t_zo.back());
                         out.t_cre.push_back(0.0);
                         out.t_cim.push_back(0.0);
+                        ++nt_emit;
                     }
                     out.g_hdr.push_back(tile_word_of(gi.xl) | ((uint32_t)nt_emit << HDR_NT_SHIFT) | (gi.imag ? HDR_IMAG : 0u));
-                    out.g_hdr.push_back(gi.word_b);
+                    out.g_hdr.push_back(0u);
                     out.g_slot.push_back(g.slot);
                     done[gi.gi] = 1;
                     --left;

@@ -27,36 +27,41 @@ struct TermView {
 };
 
 constexpr int PLAN_MAX_TILE_BITS = 13;  // the header keeps 13 bits of tile-local X mask
-constexpr int PLAN_MIN_TILE_BITS = 8;   // below this the direct kernel is used
-constexpr int PLAN_MAX_RUNS = 24;
 constexpr int PLAN_LOW_BITS = 3;        // 8 amplitudes = 128 B (c128) contiguous per gather segment
-constexpr int PLAN_REG_BITS = 3;        // tile-local bits [0, 3) index the 8 rows a thread keeps in registers
-constexpr int PLAN_U_SHIFT = 8;         // tile-local bits >= 8 are warp-uniform (row-block index)
-static_assert(PLAN_REG_BITS == PLAN_LOW_BITS, "register rows are the contiguous low amplitudes");
+constexpr int PLAN_REG_BITS = 4;        // tile-local bits [0, 4) index the 16 rows a thread keeps in registers
+constexpr int PLAN_U_SHIFT = PLAN_REG_BITS + 5;  // tile-local bits >= 9 are warp-uniform (row-block index = warp index)
+constexpr int PLAN_MIN_TILE_BITS = PLAN_U_SHIFT; // one full warp row block; below this the direct kernel is used
+constexpr int PLAN_SKIP_MIN_BIT = PLAN_REG_BITS + 3;  // a skip bit on lane bit >= 3 still idles whole quarter warps (128-bit accesses)
+constexpr int PLAN_MAX_RUNS = 24;
+static_assert(PLAN_REG_BITS >= PLAN_LOW_BITS, "register rows contain the contiguous low amplitudes");
 
 // group header word a
 constexpr uint32_t HDR_XL_MASK = 0x1fffu;   // bits 0..12: tile-local X mask in shared-memory word form, tile_word_of(xl)
-constexpr int HDR_NT_SHIFT = 13;            // bits 13..24: number of terms (<= 4095)
+constexpr int HDR_NT_SHIFT = 13;            // bits 13..24: number of staged terms (<= 4095)
 constexpr uint32_t HDR_NT_MASK = 0xfffu;
 constexpr uint32_t HDR_IMAG = 1u << 25;     // gather coefficients purely imaginary (stored in t_cre)
-// group header word b: KIND_SINGLE: bits 16..23 = register-row sign pattern of the group
-constexpr int HDR_PAT_SHIFT = 16;
+// group header word b: unused (0)
 
-// A sweep's groups are ordered into *ranges* of equal (skip bit, kind):
-//   skip bit: tile-local index (>= PLAN_U_SHIFT) of the top X bit of a Hermitian group, 0 if none.  <psi|G|psi> on one tile
-//             equals 2 Re over the rows with that bit clear, so row blocks with the bit set skip the whole range;
-//   kind:     how W(row) = sum_t c_t (-1)^{|z_t & row|} is formed for the thread's 8 register rows;
-enum { KIND_FAST = 0,     // no z bit on the register rows: W is the same for the 8 rows
-       KIND_SINGLE = 1,   // all terms share their z bits on the register rows: W = +-S by a group pattern
-       KIND_MULTI = 2,    // terms sorted by their register-row z bits: one signed sum per run, folded in with the run's pattern
-       KIND_GENERIC = 3   // one signed add per (term, row); the only kind of complex-coefficient sweeps
+// staged term word t_zl: bits 4..12 = z bits on the lane / row-block positions of the tile; bits 16..19 = z bits on the register
+// rows (v); bits 20..31 = length of the run of equal v this term starts (0 for the other terms of the run).
+constexpr uint32_t TZ_HI_MASK = ((1u << PLAN_MAX_TILE_BITS) - 1u) & ~((1u << PLAN_REG_BITS) - 1u);
+constexpr int TZ_V_SHIFT = 16, TZ_RUN_SHIFT = 20;
+
+// A sweep's groups are ordered into *ranges* of equal (skip bit, polarity, kind):
+//   skip bit: tile-local index (>= PLAN_SKIP_MIN_BIT) of the top X bit of a Hermitian group with real gather coefficients, 0 if
+//             none.  <psi|G|psi> on one tile equals 2 Re over the rows whose skip bit equals the range's polarity, so the other
+//             rows (whole warps for bits >= PLAN_U_SHIFT, whole quarter warps below) skip the range.  The planner balances the
+//             two polarities of every skip bit so that all row blocks carry the same work;
+//   kind:     how W(row) = sum_t c_t (-1)^{|z_t & row|} is formed for the thread's 16 register rows.
+enum { KIND_FAST = 0,  // no z bit on the register rows: W is the same for the 16 rows; term list padded to an even length
+       KIND_RUNS = 1   // terms sorted by their register-row z bits v: one signed sum S per run, <.> folded with (-1)^{v.r}
 };
 // range descriptor: word 0 = first group | (one past the last group) << 16 (sweep-local);
-//                   word 1 = first term (sweep-local) | kind << 16 | skip bit << 24
-constexpr int RNG_KIND_SHIFT = 16, RNG_SKIP_SHIFT = 24;
+//                   word 1 = first term (sweep-local) | kind << 16 | polarity << 18 | skip bit << 24
+constexpr int RNG_KIND_SHIFT = 16, RNG_POL_SHIFT = 18, RNG_SKIP_SHIFT = 24;
 
 // shared-memory word of tile-local index j (an involution, linear over GF(2)): see sweep.cu
-inline uint32_t tile_word_of(uint32_t j) { return j ^ ((j >> PLAN_REG_BITS) & ((1u << PLAN_REG_BITS) - 1u)); }
+inline uint32_t tile_word_of(uint32_t j) { return j ^ ((j >> PLAN_REG_BITS) & 7u); }
 
 struct PlanLimits {
     int tile_bits = 13;
@@ -98,8 +103,7 @@ struct PlanHost {
     std::vector<uint32_t> g_hdr;
     std::vector<int32_t> g_slot;
     std::vector<uint32_t> r_desc;  // two words per range
-    std::vector<uint32_t> t_zl;    // tile-local z mask, bits [0, REG_BITS) replaced by nothing (cleared); bits 16..23: sign pattern over the
-                                   // thread's 2^REG_BITS register rows, bit r = parity(z_reg & r)
+    std::vector<uint32_t> t_zl;    // staged term word, see the TZ_* constants
     std::vector<uint64_t> t_zo;    // shard-local z bits outside the tile
     std::vector<double> t_cre, t_cim;  // gather-form coefficients, rank sign folded; imag groups keep Im in t_cre
     // direct layout (class order, original term order inside a class)

@@ -24,28 +24,28 @@
 
 namespace qfe {
 
-constexpr int NT = 512;           // threads per CTA of the tile kernel
+constexpr int NT = 512;           // threads per CTA of the tile kernel: one warp per row block of 512 amplitudes
 constexpr int NW = NT / 32;
-constexpr int RB = PLAN_REG_BITS; // register-blocked rows per thread: R = 8 = the 8 contiguous low amplitudes
+constexpr int RB = PLAN_REG_BITS; // register-blocked rows per thread: R = 16 (tile-local bits 0..3)
 constexpr int R = 1 << RB;
-// shared-memory word of tile-local index j is j ^ ((j >> 3) & 7): the 8 rows of a thread sit in one 128 B line, rotated by
+// shared-memory word of tile-local index j is j ^ ((j >> 4) & 7): the 16 rows of a thread sit in two 128 B lines, rotated by
 // the low lane bits so that a quarter warp's 128-bit accesses hit 8 distinct bank groups.  The map is linear over GF(2), so
-// the partner j ^ x of row j lives at word(j) ^ word(x): one XOR per group, K (the X bits on the register rows) included.
+// the partner j ^ x of row j lives at word(j) ^ word(x): one XOR per group, the X bits on the register rows included.
 static_assert(PLAN_MIN_TILE_BITS == 5 + RB, "a tile must hold at least one full warp row block");
 static_assert(PLAN_U_SHIFT == 5 + RB, "warp-uniform tile bits start above the lane and register bits");
+static_assert((1 << (PLAN_MAX_TILE_BITS - 5 - RB)) == NW, "one warp per row block of the largest tile");
 
-// EXPECT_SAME: <psi|H|psi>, bra tile == ket tile (own rows in registers, Hermitian groups visit half the rows)
-// EXPECT:      <bra|H|ket> accumulated as rows of H|ket> then dotted with the bra rows
-// APPLY:       y (+)= H|ket>
-// BATCH:       one value per group (operator pools): <bra| G_g |ket>
-enum { MODE_EXPECT = 0, MODE_APPLY = 1, MODE_BATCH = 2, MODE_EXPECT_SAME = 3 };
+// EXPECT: <bra|H|ket>; with bra tile == ket tile the own rows come from the tile and Hermitian ranges visit half the rows
+// APPLY:  y (+)= H|ket>
+// BATCH:  one value per group (operator pools): <bra| G_g |ket>
+enum { MODE_EXPECT = 0, MODE_APPLY = 1, MODE_BATCH = 2 };
 
 template <typename real_t> struct CplxOf;
 template <> struct CplxOf<double> { using type = double2; };
 template <> struct CplxOf<float> { using type = float2; };
 
-// one staged term: coefficient (sign of the z bits outside the tile folded in per tile), the z bits on
-// lane / row-block positions, and the sign pattern over the 8 register rows (bits 16..23)
+// one staged term: coefficient (sign of the z bits outside the tile folded in per tile) and the word t_zl of plan_host.h
+// (z bits on lane / row-block positions, register-row bits v, run length)
 template <typename real_t, bool CPLX> struct TermRec;
 template <> struct __align__(16) TermRec<double, false> { double c; uint32_t zp; uint32_t pad; };
 template <> struct __align__(16) TermRec<double, true> { double c; double ci; uint32_t zp; uint32_t pad[3]; };
@@ -83,7 +83,7 @@ constexpr uint32_t SM_RNG = SM_HDR + 4096;              // 2 KB range descriptor
 constexpr uint32_t SM_SPREAD = SM_RNG + 2048;           // 1 KB tile-index -> shard-position tables
 constexpr uint32_t SM_RED = SM_SPREAD + 1024;           // block reduction scratch
 constexpr uint32_t SM_TOTAL = SM_RED + NW * 16;
-constexpr int SWEEP_MAX_TERMS = 2048, SWEEP_MAX_GROUPS = 512;  // ranges per sweep <= 6 skip bits x 4 kinds
+constexpr int SWEEP_MAX_TERMS = 2048, SWEEP_MAX_GROUPS = 512;  // ranges per sweep <= 7 skip levels x 2 polarities x 2 kinds
 constexpr int BATCH_MAX_TERMS = 1024, BATCH_MAX_GROUPS = 128;
 static_assert((size_t)NW * BATCH_MAX_GROUPS * 16 <= 32768 && BATCH_MAX_TERMS * 32 <= 32768, "batch accumulators share the term area");
 static_assert(SM_TOTAL <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
@@ -121,153 +121,178 @@ __device__ __forceinline__ float2 ld_stream(const float2* p) {
     return v;
 }
 
-// value with its sign bit XORed by bit 31 of `flip` (one 32-bit LOP on the high word)
-__device__ __forceinline__ double flip_sign(double c, uint32_t flip) {
-    return __hiloint2double(__double2hiint(c) ^ (int)(flip & 0x80000000u), __double2loint(c));
+// c with its sign flipped iff `par` is odd: adding par << 31 to the high word flips the sign bit and nothing else (one IMAD / LEA)
+__device__ __forceinline__ double sign_by_parity(double c, uint32_t par) {
+    return __hiloint2double((int)((uint32_t)__double2hiint(c) + (par << 31)), __double2loint(c));
 }
-__device__ __forceinline__ float flip_sign(float c, uint32_t flip) { return __int_as_float(__float_as_int(c) ^ (int)(flip & 0x80000000u)); }
+__device__ __forceinline__ float sign_by_parity(float c, uint32_t par) { return __uint_as_float(__float_as_uint(c) + (par << 31)); }
+
+// (-1)^{bit k of v} as a floating-point factor
+template <typename real_t> __device__ __forceinline__ real_t sigma(uint32_t v, int k);
+template <> __device__ __forceinline__ double sigma<double>(uint32_t v, int k) { return __hiloint2double((int)(0x3ff00000u | ((v >> k) << 31)), 0); }
+template <> __device__ __forceinline__ float sigma<float>(uint32_t v, int k) { return __uint_as_float(0x3f800000u | ((v >> k) << 31)); }
 
 // one shared-memory load per staged term (real-coefficient records)
-__device__ __forceinline__ void load_rec(const TermRec<double, false>* p, double& c, uint32_t& zp) {
+__device__ __forceinline__ void load_rec(const TermRec<double, false>* p, double& c, double& ci, uint32_t& zp) {
     const uint4 raw = *reinterpret_cast<const uint4*>(p);
     c = __hiloint2double((int)raw.y, (int)raw.x);
+    ci = 0.0;
     zp = raw.z;
 }
-__device__ __forceinline__ void load_rec(const TermRec<float, false>* p, float& c, uint32_t& zp) {
+__device__ __forceinline__ void load_rec(const TermRec<float, false>* p, float& c, float& ci, uint32_t& zp) {
     const uint2 raw = *reinterpret_cast<const uint2*>(p);
     c = __uint_as_float(raw.x);
+    ci = 0.0f;
     zp = raw.y;
 }
-// complex-coefficient sweeps only use the generic path, which reads the fields directly
-__device__ __forceinline__ void load_rec(const TermRec<double, true>* p, double& c, uint32_t& zp) { c = p->c; zp = p->zp; }
-__device__ __forceinline__ void load_rec(const TermRec<float, true>* p, float& c, uint32_t& zp) { c = p->c; zp = p->zp; }
-
-__device__ __forceinline__ uint32_t tile_word(uint32_t j) { return j ^ ((j >> RB) & (R - 1)); }
-
-// S = sum_t c_t (-1)^{|z_t & jhi|} over terms [t, t + nt); nt is even (the planner pads with a zero term): two independent
-// loads and sums per step
-template <typename rec_t, typename real_t>
-__device__ __forceinline__ real_t signed_sum(const rec_t* __restrict__ s_rec, int t, const int nt, const uint32_t jhi) {
-    real_t S0 = (real_t)0, S1 = (real_t)0;
-    const int te = t + nt;
-#pragma unroll 1
-    for (; t < te; t += 2) {
-        real_t c0, c1;
-        uint32_t z0, z1;
-        load_rec(s_rec + t, c0, z0);
-        load_rec(s_rec + t + 1, c1, z1);
-        S0 += flip_sign(c0, (uint32_t)__popc(z0 & jhi) << 31);
-        S1 += flip_sign(c1, (uint32_t)__popc(z1 & jhi) << 31);
-    }
-    return S0 + S1;
+__device__ __forceinline__ void load_rec(const TermRec<double, true>* p, double& c, double& ci, uint32_t& zp) {
+    const double2 cc = *reinterpret_cast<const double2*>(p);
+    c = cc.x;
+    ci = cc.y;
+    zp = p->zp;
+}
+__device__ __forceinline__ void load_rec(const TermRec<float, true>* p, float& c, float& ci, uint32_t& zp) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(p);
+    c = __uint_as_float(raw.x);
+    ci = __uint_as_float(raw.y);
+    zp = raw.z;
 }
 
-// Row work of one group for the thread's 8 rows; the partner of row r is tile word pw ^ r.
-// UNIFORM: W is the same for the 8 rows (W[0] holds it).
-template <typename real_t, bool CPLX, int MODE, bool UNIFORM>
-__device__ __forceinline__ void group_rows(const typename CplxOf<real_t>::type* __restrict__ tile, const uint32_t pw, const real_t (&W)[R], const real_t (&Wi)[R],
-                                           const bool imag, const bool half, const typename CplxOf<real_t>::type (&own)[R],
-                                           real_t (&acc_re)[R], real_t (&acc_im)[R], double& e_re, double& e_im, double& e_half) {
-    using cplx_t = typename CplxOf<real_t>::type;
-    if (MODE == MODE_EXPECT_SAME && half) {
-        // Hermitian group: the pair (b, b^x) sums to 2 Re(conj(psi_b) W psi_p); only rows with the skip bit clear get here.
-        // real W: W (a a' + b b');  imaginary W = i w: -w Im(conj(psi_b) psi_p) = w (b a' - a b')
-        real_t s0 = (real_t)0, s1 = (real_t)0, s2 = (real_t)0, s3 = (real_t)0;  // independent chains keep the FP64 pipe busy
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const cplx_t p = tile[pw ^ (uint32_t)r];
-            const real_t u = imag ? p.y : p.x, v = imag ? p.x : p.y;
-            if (UNIFORM) {
-                if (r & 1) {
-                    s2 = fma(imag ? -own[r].x : own[r].x, u, s2);
-                    s3 = fma(own[r].y, v, s3);
-                } else {
-                    s0 = fma(imag ? -own[r].x : own[r].x, u, s0);
-                    s1 = fma(own[r].y, v, s1);
-                }
-            } else {
-                const real_t t = (imag ? -own[r].x : own[r].x) * u + own[r].y * v;
-                if (r & 1)
-                    s1 = fma(W[r], t, s1);
-                else
-                    s0 = fma(W[r], t, s0);
+__device__ __forceinline__ uint32_t tile_word(uint32_t j) { return j ^ ((j >> RB) & 7u); }
+
+// S = sum_t c_t (-1)^{|z_t & jhi|} over the staged terms [t, te).  jhi only has lane / row-block bits set, so the run fields in the
+// upper half of the term word never reach the popc.  EVEN: te - t is even (KIND_FAST lists are padded): two independent chains.
+template <typename real_t, bool CPLX, bool EVEN>
+__device__ __forceinline__ void signed_sum(const TermRec<real_t, CPLX>* __restrict__ s_rec, int t, const int te, const uint32_t jhi, real_t& Sre, real_t& Sim) {
+    real_t S0 = (real_t)0, S1 = (real_t)0, I0 = (real_t)0, I1 = (real_t)0;
+    if (EVEN) {
+#pragma unroll 1
+        for (; t < te; t += 2) {
+            real_t c0, c1, d0, d1;
+            uint32_t z0, z1;
+            load_rec(s_rec + t, c0, d0, z0);
+            load_rec(s_rec + t + 1, c1, d1, z1);
+            const uint32_t p0 = (uint32_t)__popc(z0 & jhi), p1 = (uint32_t)__popc(z1 & jhi);
+            S0 += sign_by_parity(c0, p0);
+            S1 += sign_by_parity(c1, p1);
+            if (CPLX) {
+                I0 += sign_by_parity(d0, p0);
+                I1 += sign_by_parity(d1, p1);
             }
-        }
-        e_half += UNIFORM ? (double)(W[0] * ((s0 + s1) + (s2 + s3))) : (double)(s0 + s1);
-    } else if (MODE == MODE_EXPECT_SAME || (MODE == MODE_BATCH && UNIFORM)) {
-        // full complex value of sum_r conj(own_r) Wc p_r  (own = ket rows for EXPECT_SAME, bra rows for BATCH)
-        real_t sr = (real_t)0, si = (real_t)0, sr2 = (real_t)0, si2 = (real_t)0;
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const cplx_t p = tile[pw ^ (uint32_t)r];
-            if (UNIFORM) {  // sum_r conj(own_r) p_r first, the common weight afterwards
-                sr = fma(own[r].x, p.x, sr);
-                sr2 = fma(own[r].y, p.y, sr2);
-                si = fma(own[r].x, p.y, si);
-                si2 = fma(-own[r].y, p.x, si2);
-            } else {
-                const real_t cr = own[r].x * p.x + own[r].y * p.y;
-                const real_t ci = own[r].x * p.y - own[r].y * p.x;
-                if (CPLX) {
-                    sr += W[r] * cr - Wi[r] * ci;
-                    si += W[r] * ci + Wi[r] * cr;
-                } else {
-                    sr = fma(W[r], cr, sr);
-                    si = fma(W[r], ci, si);
-                }
-            }
-        }
-        sr += sr2;
-        si += si2;
-        if (UNIFORM) {
-            sr *= W[0];
-            si *= W[0];
-        }
-        if (!CPLX && imag) {  // Wc = i W
-            const real_t t = sr;
-            sr = -si;
-            si = t;
-        }
-        if (MODE == MODE_BATCH) {
-            e_re = (double)sr;
-            e_im = (double)si;
-        } else {
-            e_re += (double)sr;
-            e_im += (double)si;
         }
     } else {
-        real_t sr = (real_t)0, si = (real_t)0;
+#pragma unroll 1
+        for (; t < te; ++t) {
+            real_t c0, d0;
+            uint32_t z0;
+            load_rec(s_rec + t, c0, d0, z0);
+            const uint32_t p0 = (uint32_t)__popc(z0 & jhi);
+            S0 += sign_by_parity(c0, p0);
+            if (CPLX) I0 += sign_by_parity(d0, p0);
+        }
+    }
+    Sre = S0 + S1;
+    Sim = I0 + I1;
+}
+
+// sum_r (-1)^{v.r} f_r over N = 2^m rows with the low m bits of v: m halving steps of fused multiply-adds
+template <typename real_t, int N>
+__device__ __forceinline__ real_t fold_rows(const real_t (&f)[N], const uint32_t v) {
+    constexpr int TOP = (N == 16 ? 3 : 2);
+    real_t g[N / 2];  // f stays intact for the next run: the first step writes the half-size copy
+    {
+        const real_t s = sigma<real_t>(v, TOP);
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const cplx_t p = tile[pw ^ (uint32_t)r];
-            const real_t w = UNIFORM ? W[0] : W[r];
-            real_t t_re, t_im;
-            if (CPLX) {
-                t_re = w * p.x - Wi[r] * p.y;
-                t_im = w * p.y + Wi[r] * p.x;
-            } else if (imag) {
-                t_re = -w * p.y;
-                t_im = w * p.x;
-            } else {
-                t_re = w * p.x;
-                t_im = w * p.y;
-            }
-            if (MODE == MODE_BATCH) {
-                sr += own[r].x * t_re + own[r].y * t_im;  // conj(bra) * t
-                si += own[r].x * t_im - own[r].y * t_re;
-            } else {
-                acc_re[r] += t_re;
-                acc_im[r] += t_im;
-            }
-        }
-        if (MODE == MODE_BATCH) {
-            e_re = (double)sr;
-            e_im = (double)si;
-        }
+        for (int r = 0; r < N / 2; ++r) g[r] = fma(s, f[r + N / 2], f[r]);
+    }
+#pragma unroll
+    for (int h = N / 4, bit = TOP - 1; h >= 1; h >>= 1, --bit) {
+        const real_t s = sigma<real_t>(v, bit);
+#pragma unroll
+        for (int r = 0; r < h; ++r) g[r] = fma(s, g[r + h], g[r]);
+    }
+    return g[0];
+}
+
+// (sr, si) * Wc with Wc = S (real), i S (imag) or Sre + i Sim (CPLX)
+template <typename real_t, bool CPLX>
+__device__ __forceinline__ void times_weight(real_t& sr, real_t& si, const real_t Sre, const real_t Sim, const bool imag) {
+    if (CPLX) {
+        const real_t t = Sre * sr - Sim * si;
+        si = Sre * si + Sim * sr;
+        sr = t;
+    } else if (imag) {
+        const real_t t = -Sre * si;
+        si = Sre * sr;
+        sr = t;
+    } else {
+        sr *= Sre;
+        si *= Sre;
     }
 }
 
-// All groups of one range (same skip bit and kind) for the thread's 8 rows.
+// <own| G |tile> of one group for the thread's 16 rows: sum_r conj(own_r) Wc(r) p_r with p_r the partner of row r at tile word pw ^ r.
+template <typename real_t, bool CPLX, int KIND>
+__device__ __forceinline__ void group_value_full(const typename CplxOf<real_t>::type* __restrict__ tile, const TermRec<real_t, CPLX>* __restrict__ s_rec, const uint32_t pw,
+                                                 const int tb, const int nt, const bool imag, const uint32_t jhi,
+                                                 const typename CplxOf<real_t>::type (&own)[R], real_t& out_re, real_t& out_im) {
+    using cplx_t = typename CplxOf<real_t>::type;
+    if (KIND == KIND_FAST) {
+        real_t Sre, Sim;
+        signed_sum<real_t, CPLX, true>(s_rec, tb, tb + nt, jhi, Sre, Sim);
+        real_t a0 = (real_t)0, a1 = (real_t)0, b0 = (real_t)0, b1 = (real_t)0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const cplx_t p = tile[pw ^ (uint32_t)r];
+            a0 = fma(own[r].x, p.x, a0);  // Re conj(own) p = a a' + b b'
+            a1 = fma(own[r].y, p.y, a1);
+            b0 = fma(own[r].x, p.y, b0);  // Im conj(own) p = a b' - b a'
+            b1 = fma(-own[r].y, p.x, b1);
+        }
+        real_t sr = a0 + a1, si = b0 + b1;
+        times_weight<real_t, CPLX>(sr, si, Sre, Sim, imag);
+        out_re = sr;
+        out_im = si;
+    } else {
+        // rows in two chunks of 8 (keeps 16 products, not 32, live); the term sums of a run are formed once per chunk
+        real_t tot_re = (real_t)0, tot_im = (real_t)0;
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+            real_t fr[8], fi[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int r = 8 * ch + q;
+                const cplx_t p = tile[pw ^ (uint32_t)r];
+                fr[q] = fma(own[r].x, p.x, own[r].y * p.y);
+                fi[q] = fma(own[r].x, p.y, -own[r].y * p.x);
+            }
+            int t = tb;
+            const int te = tb + nt;
+#pragma unroll 1
+            while (t < te) {
+                const uint32_t head = s_rec[t].zp;
+                const uint32_t v = (head >> TZ_V_SHIFT) & 15u;
+                const int len = (int)(head >> TZ_RUN_SHIFT);
+                real_t Sre, Sim;
+                signed_sum<real_t, CPLX, false>(s_rec, t, t + len, jhi, Sre, Sim);
+                t += len;
+                real_t sr = fold_rows<real_t, 8>(fr, v), si = fold_rows<real_t, 8>(fi, v);
+                if (ch) {
+                    const real_t s3 = sigma<real_t>(v, 3);
+                    sr *= s3;
+                    si *= s3;
+                }
+                times_weight<real_t, CPLX>(sr, si, Sre, Sim, imag);
+                tot_re += sr;
+                tot_im += si;
+            }
+        }
+        out_re = tot_re;
+        out_im = tot_im;
+    }
+}
+
+// All groups of one range (same skip bit, polarity and kind) for the thread's 16 rows.
 template <typename real_t, bool CPLX, int MODE, int KIND>
 __device__ __forceinline__ void process_range(const typename CplxOf<real_t>::type* __restrict__ tile, const TermRec<real_t, CPLX>* __restrict__ s_rec,
                                               const uint2* __restrict__ s_hdr, double2* __restrict__ s_acc_warp, const int g0, const int g1, int tb,
@@ -275,79 +300,156 @@ __device__ __forceinline__ void process_range(const typename CplxOf<real_t>::typ
                                               const typename CplxOf<real_t>::type (&own)[R], real_t (&acc_re)[R], real_t (&acc_im)[R],
                                               double& e_re, double& e_im, double& e_half) {
     using cplx_t = typename CplxOf<real_t>::type;
-    using rec_t = TermRec<real_t, CPLX>;
-    for (int g = g0; g < g1; ++g) {
-        const uint2 hdr = s_hdr[g];
-        const uint32_t pw = w0 ^ (hdr.x & HDR_XL_MASK);  // header keeps the X mask already in word form
-        const int nt = (int)((hdr.x >> HDR_NT_SHIFT) & HDR_NT_MASK);
-        const bool imag = hdr.x & HDR_IMAG;
-        real_t W[R], Wi[R];  // W(row) = sum_t c_t (-1)^{|z_t & row|}
-#pragma unroll
-        for (int r = 0; r < R; ++r) Wi[r] = (real_t)0;
-        if (KIND == KIND_FAST) {
-            W[0] = signed_sum<rec_t, real_t>(s_rec, tb, nt, jhi);
-#pragma unroll
-            for (int r = 1; r < R; ++r) W[r] = W[0];
-        } else if (KIND == KIND_SINGLE) {
-            const real_t S = signed_sum<rec_t, real_t>(s_rec, tb, nt, jhi);
-            const uint32_t pat = hdr.y >> HDR_PAT_SHIFT;
-#pragma unroll
-            for (int r = 0; r < R; ++r) W[r] = flip_sign(S, pat << (31 - r));
-        } else if (KIND == KIND_MULTI) {
-            // terms sorted by their register-row z bits: one signed sum per run of equal bits, folded into the 8 rows with the
-            // run's sign pattern (kept in bits 16..23 of the term word)
-#pragma unroll
-            for (int r = 0; r < R; ++r) W[r] = (real_t)0;
-            real_t S = (real_t)0;
-            uint32_t cur = s_rec[tb].zp >> 16;
 #pragma unroll 1
-            for (int t = tb; t < tb + nt; ++t) {
-                real_t c;
-                uint32_t z;
-                load_rec(s_rec + t, c, z);
-                if ((z >> 16) != cur) {  // warp-uniform
+    for (int g = g0; g < g1; ++g) {
+        const uint32_t hdr = s_hdr[g].x;
+        const uint32_t pw = w0 ^ (hdr & HDR_XL_MASK);  // header keeps the X mask already in word form
+        const int nt = (int)((hdr >> HDR_NT_SHIFT) & HDR_NT_MASK);
+        const bool imag = hdr & HDR_IMAG;
+        if (MODE == MODE_EXPECT && half) {
+            // Hermitian group with real W: the pair (b, b^x) sums to 2 Re(conj(psi_b) W psi_p) = 2 W (a a' + b b'); only rows whose
+            // skip bit equals the range polarity get here.
+            if (KIND == KIND_FAST) {
+                real_t S, Si;
+                signed_sum<real_t, false, true>(reinterpret_cast<const TermRec<real_t, false>*>(s_rec), tb, tb + nt, jhi, S, Si);
+                real_t a0 = (real_t)0, a1 = (real_t)0, a2 = (real_t)0, a3 = (real_t)0;  // independent chains keep the FP64 pipe busy
 #pragma unroll
-                    for (int r = 0; r < R; ++r) W[r] += flip_sign(S, cur << (31 - r));
-                    S = (real_t)0;
-                    cur = z >> 16;
+                for (int r = 0; r < R; ++r) {
+                    const cplx_t p = tile[pw ^ (uint32_t)r];
+                    if (r & 1) {
+                        a2 = fma(own[r].x, p.x, a2);
+                        a3 = fma(own[r].y, p.y, a3);
+                    } else {
+                        a0 = fma(own[r].x, p.x, a0);
+                        a1 = fma(own[r].y, p.y, a1);
+                    }
                 }
-                S += flip_sign(c, (uint32_t)__popc(z & jhi) << 31);
+                e_half += (double)S * (double)((a0 + a1) + (a2 + a3));
+            } else {
+                real_t f[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const cplx_t p = tile[pw ^ (uint32_t)r];
+                    f[r] = fma(own[r].x, p.x, own[r].y * p.y);
+                }
+                int t = tb;
+                const int te = tb + nt;
+                real_t tot = (real_t)0;
+#pragma unroll 1
+                while (t < te) {
+                    const uint32_t head = s_rec[t].zp;
+                    const uint32_t v = (head >> TZ_V_SHIFT) & 15u;
+                    const int len = (int)(head >> TZ_RUN_SHIFT);
+                    real_t S, Si;
+                    signed_sum<real_t, false, false>(reinterpret_cast<const TermRec<real_t, false>*>(s_rec), t, t + len, jhi, S, Si);
+                    t += len;
+                    tot = fma(S, fold_rows<real_t, R>(f, v), tot);
+                }
+                e_half += (double)tot;
             }
+        } else if (MODE == MODE_EXPECT || MODE == MODE_BATCH) {
+            real_t sr, si;
+            group_value_full<real_t, CPLX, KIND>(tile, s_rec, pw, tb, nt, imag, jhi, own, sr, si);
+            if (MODE == MODE_EXPECT) {
+                e_re += (double)sr;
+                e_im += (double)si;
+            } else {
+                double g_re = (double)sr, g_im = (double)si;
 #pragma unroll
-            for (int r = 0; r < R; ++r) W[r] += flip_sign(S, cur << (31 - r));
-        } else {
+                for (int d = 16; d > 0; d >>= 1) {
+                    g_re += __shfl_down_sync(0xffffffffu, g_re, d);
+                    g_im += __shfl_down_sync(0xffffffffu, g_im, d);
+                }
+                if ((threadIdx.x & 31) == 0) {  // only this warp writes its own row of the accumulators: deterministic
+                    double2 cur = s_acc_warp[g];
+                    cur.x += g_re;
+                    cur.y += g_im;
+                    s_acc_warp[g] = cur;
+                }
+            }
+        } else {  // MODE_APPLY: acc_r += Wc(r) p_r
+            if (KIND == KIND_FAST) {
+                real_t Sre, Sim;
+                signed_sum<real_t, CPLX, true>(s_rec, tb, tb + nt, jhi, Sre, Sim);
+                // Wc = wr + i wi
+                const real_t wr = (!CPLX && imag) ? (real_t)0 : Sre;
+                const real_t wi = CPLX ? Sim : (imag ? Sre : (real_t)0);
 #pragma unroll
-            for (int r = 0; r < R; ++r) W[r] = (real_t)0;
-            for (int t = tb; t < tb + nt; ++t) {
-                const rec_t rec = s_rec[t];
-                // sign of row r: parity of z over the lane / row-block bits XOR the register-row pattern
-                const uint32_t m = (rec.zp >> 16) ^ (0u - (uint32_t)(__popc(rec.zp & jhi) & 1));
+                for (int r = 0; r < R; ++r) {
+                    const cplx_t p = tile[pw ^ (uint32_t)r];
+                    if (CPLX) {
+                        acc_re[r] += wr * p.x - wi * p.y;
+                        acc_im[r] += wr * p.y + wi * p.x;
+                    } else if (imag) {
+                        acc_re[r] = fma(-wi, p.y, acc_re[r]);
+                        acc_im[r] = fma(wi, p.x, acc_im[r]);
+                    } else {
+                        acc_re[r] = fma(wr, p.x, acc_re[r]);
+                        acc_im[r] = fma(wr, p.y, acc_im[r]);
+                    }
+                }
+            } else {
 #pragma unroll
-                for (int r = 0; r < R; ++r) W[r] += flip_sign(rec.c, m << (31 - r));
-                if constexpr (CPLX) {
+                for (int ch = 0; ch < 2; ++ch) {
+                    real_t W[8], Wi[8];
 #pragma unroll
-                    for (int r = 0; r < R; ++r) Wi[r] += flip_sign(rec.ci, m << (31 - r));
+                    for (int q = 0; q < 8; ++q) W[q] = Wi[q] = (real_t)0;
+                    int t = tb;
+                    const int te = tb + nt;
+#pragma unroll 1
+                    while (t < te) {
+                        const uint32_t head = s_rec[t].zp;
+                        const uint32_t v = (head >> TZ_V_SHIFT) & 15u;
+                        const int len = (int)(head >> TZ_RUN_SHIFT);
+                        real_t Sre, Sim;
+                        signed_sum<real_t, CPLX, false>(s_rec, t, t + len, jhi, Sre, Sim);
+                        t += len;
+                        if (ch) {
+                            const real_t s3 = sigma<real_t>(v, 3);
+                            Sre *= s3;
+                            Sim *= s3;
+                        }
+                        // W(q) += S (-1)^{v.q}: unfold the three low bits
+                        const real_t s0 = sigma<real_t>(v, 0), s1 = sigma<real_t>(v, 1), s2 = sigma<real_t>(v, 2);
+                        real_t e[8];
+                        e[0] = Sre;
+                        e[1] = s0 * e[0];
+                        e[2] = s1 * e[0];
+                        e[3] = s1 * e[1];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) e[4 + q] = s2 * e[q];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) W[q] += e[q];
+                        if (CPLX) {
+                            e[0] = Sim;
+                            e[1] = s0 * e[0];
+                            e[2] = s1 * e[0];
+                            e[3] = s1 * e[1];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) e[4 + q] = s2 * e[q];
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) Wi[q] += e[q];
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int r = 8 * ch + q;
+                        const cplx_t p = tile[pw ^ (uint32_t)r];
+                        if (CPLX) {
+                            acc_re[r] += W[q] * p.x - Wi[q] * p.y;
+                            acc_im[r] += W[q] * p.y + Wi[q] * p.x;
+                        } else if (imag) {
+                            acc_re[r] = fma(-W[q], p.y, acc_re[r]);
+                            acc_im[r] = fma(W[q], p.x, acc_im[r]);
+                        } else {
+                            acc_re[r] = fma(W[q], p.x, acc_re[r]);
+                            acc_im[r] = fma(W[q], p.y, acc_im[r]);
+                        }
+                    }
                 }
             }
         }
         tb += nt;
-        if (MODE == MODE_BATCH) {
-            double g_re = 0.0, g_im = 0.0;
-            group_rows<real_t, CPLX, MODE, KIND == KIND_FAST>(tile, pw, W, Wi, imag, false, own, acc_re, acc_im, g_re, g_im, e_half);
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) {
-                g_re += __shfl_down_sync(0xffffffffu, g_re, d);
-                g_im += __shfl_down_sync(0xffffffffu, g_im, d);
-            }
-            if ((threadIdx.x & 31) == 0) {  // only this warp writes its own row of the accumulators: deterministic
-                double2 cur = s_acc_warp[g];
-                cur.x += g_re;
-                cur.y += g_im;
-                s_acc_warp[g] = cur;
-            }
-        } else {
-            group_rows<real_t, CPLX, MODE, KIND == KIND_FAST>(tile, pw, W, Wi, imag, half, own, acc_re, acc_im, e_re, e_im, e_half);
-        }
     }
 }
 
@@ -367,7 +469,7 @@ __global__ void __launch_bounds__(NT, 1) tile_sweep_kernel(const __grid_constant
     double2* s_acc = reinterpret_cast<double2*>(smem + SM_ACC);
     double2* s_red = reinterpret_cast<double2*>(smem + SM_RED);
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5;
     const cplx_t* __restrict__ ket = reinterpret_cast<const cplx_t*>(a.ket);
     const cplx_t* __restrict__ bra = reinterpret_cast<const cplx_t*>(a.bra);
     cplx_t* __restrict__ yout = reinterpret_cast<cplx_t*>(a.out_vec);
@@ -382,7 +484,10 @@ __global__ void __launch_bounds__(NT, 1) tile_sweep_kernel(const __grid_constant
 
     const int low = a.low_bits;
     const uint32_t lowmask = (1u << low) - 1u;
-    const int row_blocks = 1 << (k - 5 - RB);  // warp-level row blocks of 256 amplitudes
+    // one warp per row block of 512 amplitudes: thread tid owns the 16 rows jhi | r
+    const bool active = warp < (1 << (k - 5 - RB));
+    const uint32_t jhi = (uint32_t)tid << RB;  // tile-local index of row 0 (lane and row-block bits)
+    const uint32_t w0 = tile_word(jhi);        // its shared-memory word; row r is at w0 ^ r
     double e_re = 0.0, e_im = 0.0, e_half = 0.0;
 
     for (unsigned long long tile_id = blockIdx.x; tile_id < a.n_tiles; tile_id += gridDim.x) {
@@ -399,22 +504,21 @@ __global__ void __launch_bounds__(NT, 1) tile_sweep_kernel(const __grid_constant
         __syncthreads();  // previous tile fully consumed (also orders the one-time tables)
         {
             const uint64_t kbase = base ^ a.ket_xor;
-            // 2^k / NT amplitudes per thread, 4 independent 128-bit loads in flight per step
-            for (uint32_t i0 = tid; i0 < tile_amps; i0 += 4 * NT) {
-                cplx_t v[4];
+            // 2^k / NT amplitudes per thread (a power of two); full tiles keep 8 independent 128-bit loads in flight per step
+            if (tile_amps >= 8 * NT) {
+                for (uint32_t i0 = tid; i0 < tile_amps; i0 += 8 * NT) {
+                    cplx_t v[8];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const uint32_t idx = i0 + u * NT;
-                    if (idx < tile_amps) {
-                        const uint64_t g = kbase | (idx & lowmask) | s_spread[(idx >> low) & 63] | s_spread[64 + ((idx >> (low + 6)) & 63)];
-                        v[u] = ld_stream(ket + g);
+                    for (int u = 0; u < 8; ++u) {
+                        const uint32_t idx = i0 + u * NT;
+                        v[u] = ld_stream(ket + (kbase | (idx & lowmask) | s_spread[(idx >> low) & 63] | s_spread[64 + ((idx >> (low + 6)) & 63)]));
                     }
-                }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const uint32_t idx = i0 + u * NT;
-                    if (idx < tile_amps) tile[tile_word(idx)] = v[u];
+                    for (int u = 0; u < 8; ++u) tile[tile_word(i0 + u * NT)] = v[u];
                 }
+            } else {
+                for (uint32_t idx = tid; idx < tile_amps; idx += NT)
+                    tile[tile_word(idx)] = ld_stream(ket + (kbase | (idx & lowmask) | s_spread[(idx >> low) & 63] | s_spread[64 + ((idx >> (low + 6)) & 63)]));
             }
             // coefficients with the sign of the z bits outside the tile (constant over the tile)
             for (int t = tid; t < nT; t += NT) {
@@ -429,21 +533,13 @@ __global__ void __launch_bounds__(NT, 1) tile_sweep_kernel(const __grid_constant
         }
         __syncthreads();
 
-        // Row blocks are dealt to warps in complementary pairs (u, ~u): a Hermitian range is skipped by the row blocks that
-        // have its top X bit set, so block u and its complement together always carry the same amount of work.
-        for (int it = warp; it < row_blocks; it += NW) {
-            const int half_rb = row_blocks >> 1;
-            const int u = (row_blocks == 1) ? 0 : ((it < half_rb) ? it : (row_blocks - 1 - (it - half_rb)));
-            const uint32_t jhi = (((uint32_t)u << 5) | (uint32_t)lane) << RB;  // tile-local index of row 0 (lane and row-block bits)
-            const uint32_t w0 = tile_word(jhi);                                // its shared-memory word; row r is at w0 ^ r
+        if (active) {
             real_t acc_re[R], acc_im[R];
             cplx_t own[R];
+            if (MODE == MODE_APPLY) {
 #pragma unroll
-            for (int r = 0; r < R; ++r) acc_re[r] = acc_im[r] = (real_t)0;
-            if (MODE == MODE_EXPECT_SAME) {
-#pragma unroll
-                for (int r = 0; r < R; ++r) own[r] = tile[w0 ^ (uint32_t)r];
-            } else if (MODE == MODE_BATCH) {
+                for (int r = 0; r < R; ++r) acc_re[r] = acc_im[r] = (real_t)0;
+            } else {
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     if (a.same_tile) {
@@ -455,61 +551,44 @@ __global__ void __launch_bounds__(NT, 1) tile_sweep_kernel(const __grid_constant
                 }
             }
             double2* s_acc_warp = s_acc + (size_t)warp * nG;
+#pragma unroll 1
             for (int ri = 0; ri < nR; ++ri) {
                 const uint2 d = s_rng[ri];
                 const uint32_t skipbit = d.y >> RNG_SKIP_SHIFT;
                 bool half = false;
-                if (MODE == MODE_EXPECT_SAME) {
-                    half = skipbit != 0;
-                    if (half && ((jhi >> skipbit) & 1u)) continue;  // warp-uniform: the partner row block handles these pairs
+                if (MODE == MODE_EXPECT) {
+                    half = a.same_tile && skipbit != 0;
+                    // the rows with the other polarity are the partners of these pairs (whole warps for row-block bits, whole
+                    // quarter warps for the two top lane bits)
+                    if (half && (((jhi >> skipbit) ^ (d.y >> RNG_POL_SHIFT)) & 1u)) continue;
                 }
                 const int g0 = (int)(d.x & 0xffffu), g1 = (int)(d.x >> 16), t0 = (int)(d.y & 0xffffu);
-#define QFE_RANGE(KIND_)                                                                                                                 \
-    case KIND_:                                                                                                                          \
-        process_range<real_t, CPLX, MODE, KIND_>(tile, s_rec, s_hdr, s_acc_warp, g0, g1, t0, w0, jhi, half, own, acc_re, acc_im, e_re, e_im, \
-                                                 e_half);                                                                                \
-        break;
-                if constexpr (CPLX) {
-                    process_range<real_t, CPLX, MODE, KIND_GENERIC>(tile, s_rec, s_hdr, s_acc_warp, g0, g1, t0, w0, jhi, half, own, acc_re, acc_im,
-                                                                    e_re, e_im, e_half);
-                } else {
-                    switch ((d.y >> RNG_KIND_SHIFT) & 3u) {
-                        QFE_RANGE(KIND_FAST)
-                        QFE_RANGE(KIND_SINGLE)
-                        QFE_RANGE(KIND_MULTI)
-                        QFE_RANGE(KIND_GENERIC)
-                        default: break;
-                    }
-                }
-#undef QFE_RANGE
+                if (((d.y >> RNG_KIND_SHIFT) & 3u) == KIND_FAST)
+                    process_range<real_t, CPLX, MODE, KIND_FAST>(tile, s_rec, s_hdr, s_acc_warp, g0, g1, t0, w0, jhi, half, own, acc_re, acc_im, e_re, e_im, e_half);
+                else
+                    process_range<real_t, CPLX, MODE, KIND_RUNS>(tile, s_rec, s_hdr, s_acc_warp, g0, g1, t0, w0, jhi, half, own, acc_re, acc_im, e_re, e_im, e_half);
             }
-            if (MODE == MODE_EXPECT || MODE == MODE_APPLY) {
+            if (MODE == MODE_APPLY) {
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     const uint32_t j = jhi | (uint32_t)r;
                     const uint64_t gidx = base | (j & lowmask) | s_spread[(j >> low) & 63] | s_spread[64 + ((j >> (low + 6)) & 63)];
-                    if (MODE == MODE_EXPECT) {
-                        const cplx_t b = a.same_tile ? tile[w0 ^ (uint32_t)r] : bra[gidx];
-                        e_re += (double)b.x * (double)acc_re[r] + (double)b.y * (double)acc_im[r];
-                        e_im += (double)b.x * (double)acc_im[r] - (double)b.y * (double)acc_re[r];
+                    cplx_t y;
+                    if (a.accumulate) {
+                        y = yout[gidx];
+                        y.x += acc_re[r];
+                        y.y += acc_im[r];
                     } else {
-                        cplx_t y;
-                        if (a.accumulate) {
-                            y = yout[gidx];
-                            y.x += acc_re[r];
-                            y.y += acc_im[r];
-                        } else {
-                            y.x = acc_re[r];
-                            y.y = acc_im[r];
-                        }
-                        yout[gidx] = y;
+                        y.x = acc_re[r];
+                        y.y = acc_im[r];
                     }
+                    yout[gidx] = y;
                 }
             }
         }
     }
 
-    if (MODE == MODE_EXPECT || MODE == MODE_EXPECT_SAME) {
+    if (MODE == MODE_EXPECT) {
         double2 tot = block_reduce_sum(make_double2(e_re + 2.0 * e_half, e_im), s_red);
         if (tid == 0) a.partials[blockIdx.x] = tot;
     } else if (MODE == MODE_BATCH) {
@@ -743,8 +822,6 @@ static int run_class_reduce(qfe_ctx* ctx, const qfe_plan* p, int ci, const void*
             const size_t smem = sweep_smem_bytes(sw, a.n_terms, a.n_groups, dtype, batch);
             if (batch)
                 QFE_TRY(launch_tile_d<MODE_BATCH>(ctx, a, grid, smem, sw.complex_w, dtype));
-            else if (a.same_tile)
-                QFE_TRY(launch_tile_d<MODE_EXPECT_SAME>(ctx, a, grid, smem, sw.complex_w, dtype));
             else
                 QFE_TRY(launch_tile_d<MODE_EXPECT>(ctx, a, grid, smem, sw.complex_w, dtype));
             reduce_partials<<<(n_ranges + 3) / 4, 128, 0, s>>>(a.partials, n_ranges, grid, d_vals + vpos);

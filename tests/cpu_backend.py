@@ -37,7 +37,7 @@ def make_terms(nqbits, x, z, c, constant=0.0, owner=None, n_slots=1):
 
 
 class CpuBackend:
-    def __init__(self, tile_bits=8):
+    def __init__(self, tile_bits=9):
         self.lib = _lib()
         self.tile_bits = tile_bits
 

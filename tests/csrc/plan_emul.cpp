@@ -44,7 +44,7 @@ extern "C" int plan_emul_run(int n, int64_t T, const uint64_t* x, const uint64_t
     // every group of every class must be covered by exactly one sweep
     {
         size_t ng_tiled = p.g_hdr.size() / 2, ng_direct = p.dg_slot.size();
-        if (ng_tiled != ng_direct || p.t_zl.size() < p.d_x.size() || p.t_zl.size() > p.d_x.size() + ng_direct) return 3;  // + even-length padding
+        if (ng_tiled != ng_direct || p.t_zl.size() < p.d_x.size() || p.t_zl.size() > p.d_x.size() + ng_direct) return 3;  // + even-length padding of KIND_FAST groups
     }
     for (const ClassHost& cls : p.classes) {
         if (cls.x_hi != x_hi) continue;
@@ -81,51 +81,47 @@ extern "C" int plan_emul_run(int n, int64_t T, const uint64_t* x, const uint64_t
                         const uint32_t d0 = p.r_desc[2 * ri], d1 = p.r_desc[2 * ri + 1];
                         const int g0 = (int)(d0 & 0xffffu), g1 = (int)(d0 >> 16);
                         const int kind = (int)((d1 >> RNG_KIND_SHIFT) & 3u);
+                        const uint32_t pol = (d1 >> RNG_POL_SHIFT) & 1u;
                         const uint32_t skipbit = d1 >> RNG_SKIP_SHIFT;
                         if (g0 != g_expect || (int64_t)(d1 & 0xffffu) != t_expect || g1 <= g0) return 10;  // ranges tile the sweep's groups in order
-                        if (skipbit && (skipbit < (uint32_t)PLAN_U_SHIFT || skipbit >= (uint32_t)s.k || s.ket_xor != 0)) return 11;
+                        if (skipbit && (skipbit < (uint32_t)PLAN_SKIP_MIN_BIT || skipbit >= (uint32_t)s.k || s.ket_xor != 0)) return 11;
+                        if (kind != KIND_FAST && kind != KIND_RUNS) return 12;
                         int64_t tb = s.term_begin + t_expect;
                         for (int gl = g0; gl < g1; ++gl) {
                             const int g = s.group_begin + gl;
-                            const uint32_t ha = p.g_hdr[2 * g], hb = p.g_hdr[2 * g + 1];
+                            const uint32_t ha = p.g_hdr[2 * g];
                             const uint32_t xl = tile_word_of(ha & HDR_XL_MASK);  // the header keeps the X mask in word form (an involution)
                             const int nt = (int)((ha >> HDR_NT_SHIFT) & HDR_NT_MASK);
                             const bool imag = ha & HDR_IMAG;
-                            if (skipbit && (31 - __builtin_clz(xl)) != (int)skipbit) return 13;  // the skip bit is the top X bit
+                            if (skipbit && ((31 - __builtin_clz(xl)) != (int)skipbit || imag)) return 13;  // the skip bit is the top X bit
                             cplx w(0.0, 0.0);
-                            int counts[8] = {0};
-                            uint32_t prev_pat = 0;
-                            for (int64_t tt = tb; tt < tb + nt; ++tt) {
-                                const uint32_t zl = p.t_zl[tt] & 0xffffu, pat = (p.t_zl[tt] >> 16) & 0xffu;
-                                if (zl & 7u) return 14;  // register bits live in the pattern only
-                                // pattern -> z bits on the register rows: bit i of zreg = pattern bit (1 << i)
-                                const uint32_t zreg = ((pat >> 1) & 1u) | (((pat >> 2) & 1u) << 1) | (((pat >> 4) & 1u) << 2);
-                                counts[zreg]++;
-                                if (kind == KIND_FAST && zreg != 0) return 15;
-                                if (kind == KIND_SINGLE && (pat != ((hb >> HDR_PAT_SHIFT) & 0xffu) || zreg == 0)) return 16;
-                                if (kind == KIND_MULTI && tt > tb && pat != prev_pat && zreg < (uint32_t)0) return 17;
-                                prev_pat = pat;
-                                const int par = (__builtin_popcount(zl & j) + (int)((pat >> (j & 7u)) & 1u) + __builtin_popcountll(p.t_zo[tt] & base)) & 1;
-                                cplx cc = imag ? cplx(0.0, p.t_cre[tt]) : cplx(p.t_cre[tt], p.t_cim[tt]);
-                                w += par ? -cc : cc;
-                            }
-                            if (kind == KIND_MULTI) {
-                                // sorted by zreg with the advertised 4-bit counts
-                                uint32_t last = 0;
-                                for (int64_t tt = tb; tt < tb + nt; ++tt) {
-                                    const uint32_t pat = (p.t_zl[tt] >> 16) & 0xffu;
-                                    const uint32_t zreg = ((pat >> 1) & 1u) | (((pat >> 2) & 1u) << 1) | (((pat >> 4) & 1u) << 2);
-                                    if (zreg < last) return 17;
-                                    last = zreg;
+                            // walk the runs exactly as the kernel does: the first term of a run carries its length
+                            int64_t tt = tb;
+                            uint32_t last_v = 0;
+                            bool first_run = true;
+                            while (tt < tb + nt) {
+                                const uint32_t head = p.t_zl[tt];
+                                const uint32_t v = (head >> TZ_V_SHIFT) & 15u, len = head >> TZ_RUN_SHIFT;
+                                if (len == 0 || tt + len > tb + nt) return 14;
+                                if (!first_run && v <= last_v) return 17;  // runs ascend in v
+                                if (kind == KIND_FAST && (v != 0 || len != (uint32_t)nt || (nt & 1))) return 15;
+                                for (uint32_t q = 0; q < len; ++q) {
+                                    const uint32_t w32 = p.t_zl[tt + q];
+                                    if (((w32 >> TZ_V_SHIFT) & 15u) != v || (q > 0 && (w32 >> TZ_RUN_SHIFT) != 0)) return 16;
+                                    if (w32 & 0xffffu & ~TZ_HI_MASK) return 18;  // register bits live in the v field only
+                                    const int par = (__builtin_popcount(w32 & TZ_HI_MASK & j) + __builtin_popcount(v & j) + __builtin_popcountll(p.t_zo[tt + q] & base)) & 1;
+                                    cplx cc = imag ? cplx(0.0, p.t_cre[tt + q]) : cplx(p.t_cre[tt + q], p.t_cim[tt + q]);
+                                    w += par ? -cc : cc;
                                 }
+                                last_v = v;
+                                first_run = false;
+                                tt += len;
                             }
-                            if ((kind != KIND_GENERIC) && s.complex_w) return 19;
-                            if (nt & 1) return 20;  // staged term lists are padded to an even length
                             tb += nt;
                             const cplx contrib = w * tile[j ^ xl];
                             acc_row += contrib;
                             if (same && skipbit) {
-                                if (!((j >> skipbit) & 1u)) out[p.g_slot[g]] += 2.0 * std::real(std::conj(bra[row]) * contrib);
+                                if (((j >> skipbit) & 1u) == pol) out[p.g_slot[g]] += 2.0 * std::real(std::conj(bra[row]) * contrib);
                             } else {
                                 out[p.g_slot[g]] += std::conj(bra[row]) * contrib;
                             }
@@ -194,14 +190,14 @@ extern "C" int plan_emul_dump(int n, int64_t T, const uint64_t* x, const uint64_
     if (build_plan(v, n_local, shard, lim, p, &err) != 0) return 1;
     FILE* f = fopen(path, "w");
     if (!f) return 2;
-    fprintf(f, "sweep,range,kind,skipbit,group,nt,xword,imag,tile_mask\n");
+    fprintf(f, "sweep,range,kind,skipbit,pol,group,nt,xword,imag,tile_mask\n");
     for (size_t si = 0; si < p.sweeps.size(); ++si) {
         const SweepHost& s = p.sweeps[si];
         for (int r = s.range_begin; r < s.range_end; ++r) {
             const uint32_t d0 = p.r_desc[2 * r], d1 = p.r_desc[2 * r + 1];
             for (uint32_t g = (d0 & 0xffffu); g < (d0 >> 16); ++g) {
                 const uint32_t h = p.g_hdr[2 * (s.group_begin + g)];
-                fprintf(f, "%zu,%d,%u,%u,%u,%u,%u,%u,%llu\n", si, r - s.range_begin, (d1 >> RNG_KIND_SHIFT) & 3u, d1 >> RNG_SKIP_SHIFT, g,
+                fprintf(f, "%zu,%d,%u,%u,%u,%u,%u,%u,%u,%llu\n", si, r - s.range_begin, (d1 >> RNG_KIND_SHIFT) & 3u, d1 >> RNG_SKIP_SHIFT, (d1 >> RNG_POL_SHIFT) & 1u, g,
                         (h >> HDR_NT_SHIFT) & HDR_NT_MASK, h & HDR_XL_MASK, (h & HDR_IMAG) ? 1u : 0u, (unsigned long long)s.tile_mask);
             }
         }

@@ -61,7 +61,7 @@ def _molecule(m, enc, constant=0.0):
 
 
 @pytest.mark.parametrize("enc", ["jordan-wigner", "bravyi-kitaev", "parity"])
-@pytest.mark.parametrize("tile_bits", [8, 10, 12])
+@pytest.mark.parametrize("tile_bits", [9, 10, 12])
 def test_unsharded_plan_reproduces_apply_and_expectation(emul, enc, tile_bits):
     n = 12
     x, z, c, k = _molecule(6, enc, constant=0.4)
@@ -79,7 +79,7 @@ def test_unsharded_plan_reproduces_apply_and_expectation(emul, enc, tile_bits):
     assert 1 <= stats[0] <= n_groups
 
 
-@pytest.mark.parametrize("n_local", [8, 10])
+@pytest.mark.parametrize("n_local", [9, 10])
 def test_sharded_classes_recombine(emul, n_local):
     n = 12
     x, z, c, k = _molecule(6, "bravyi-kitaev", constant=-0.3)
@@ -93,7 +93,7 @@ def test_sharded_classes_recombine(emul, n_local):
         for x_hi in range(1 << g):
             own = psi[r << n_local : (r + 1) << n_local]
             partner = psi[(r ^ x_hi) << n_local : ((r ^ x_hi) + 1) << n_local]
-            out, y, _ = _run(emul, n, x, z, c, np.zeros(len(x)), 1, [k], n_local, r, 8, x_hi, own, partner)
+            out, y, _ = _run(emul, n, x, z, c, np.zeros(len(x)), 1, [k], n_local, r, 9, x_hi, own, partner)
             phi[r << n_local : (r + 1) << n_local] += y
             total += out[0]
     assert np.max(np.abs(phi - want_phi)) <= 1e-12 * np.max(np.abs(want_phi))
@@ -120,7 +120,7 @@ def test_wide_masks_and_capacity_splits(emul):
     c = c[: len(recs)]
     consts = np.array([0.5, 0.0, -0.25j])
     psi, bra = _state(n, 4), _state(n, 5)
-    out, y, stats = _run(emul, n, x, z, c, owner, 3, consts, n, 0, 8, 0, bra, psi, max_terms=64, max_groups=16)
+    out, y, stats = _run(emul, n, x, z, c, owner, 3, consts, n, 0, 9, 0, bra, psi, max_terms=64, max_groups=16)
     want_total = np.zeros_like(psi)
     for s in range(3):
         sel = owner == s

@@ -36,11 +36,11 @@ def _worker(rank, world, port, out_dir):
         from myqlm_fermion_b200.sharded import ShardedEngine
         from oracle import models, spin, transforms
 
-        n = 10
+        n = 12  # shards of 2^10 (world 4) or 2^11 amplitudes: at least one 2^9 tile
         one, two = models.synthetic_integrals(n // 2, seed=1234)
         hpq, hpqrs = models.convert_to_h_integrals(one, two)
         x, z, c, k = transforms.transform(n, models.electronic_terms(hpq, hpqrs), 0.3, "bravyi-kitaev").canonical()
-        be = CpuBackend(tile_bits=8)
+        be = CpuBackend(tile_bits=9)
         se = ShardedEngine(be, n)
         assert se.n_local == n - (world.bit_length() - 1)
         h_terms = make_terms(n, x, z, c, constant=k)
@@ -72,9 +72,9 @@ def _worker(rank, world, port, out_dir):
         assert np.max(np.abs(g - want_g)) <= 1e-11 * max(1.0, np.max(np.abs(want_g)))
 
         # sharded Lanczos on a small Hubbard chain vs dense eigvalsh
-        n2 = 10
-        t_mat = np.zeros((5, 5))
-        for i in range(4):
+        n2 = 12
+        t_mat = np.zeros((6, 6))
+        for i in range(5):
             t_mat[i, i + 1] = t_mat[i + 1, i] = -1.0
         a, b = models.hubbard_integrals(t_mat, 4.0, 2.0)
         x2, z2, c2, k2 = transforms.transform(n2, models.electronic_terms(a, b), 0.0, "jordan-wigner").canonical()
