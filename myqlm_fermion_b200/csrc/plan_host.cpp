@@ -37,23 +37,9 @@ inline void gather_coeff(const TermView& t, int64_t i, int n_local, int shard, d
     }
 }
 
+// outer-mask runs and tile count of a sweep whose tile mask and pos[] are set
 void finish_sweep_geometry(SweepHost& s, int n_local) {
     const uint64_t all = n_local >= 64 ? ~uint64_t(0) : ((uint64_t(1) << n_local) - 1);
-    // free positions of L above the low bits, ascending -> spread tables
-    int pos[PLAN_MAX_TILE_BITS];
-    int np = 0;
-    for (int b = s.low_bits; b < n_local; ++b)
-        if ((s.tile_mask >> b) & 1) pos[np++] = b;
-    for (int tbl = 0; tbl < 2; ++tbl)
-        for (uint32_t v = 0; v < 64; ++v) {
-            uint64_t m = 0;
-            for (int i = 0; i < 6; ++i) {
-                int idx = tbl * 6 + i;
-                if (idx < np && ((v >> i) & 1)) m |= uint64_t(1) << pos[idx];
-            }
-            s.spread[tbl][v] = m;
-        }
-    // runs of the outer mask
     const uint64_t outer = all & ~s.tile_mask;
     s.n_runs = 0;
     int b = 0;
@@ -75,15 +61,9 @@ void finish_sweep_geometry(SweepHost& s, int n_local) {
 }  // namespace
 
 uint32_t compress_to_tile(const SweepHost& s, uint64_t mask) {
-    uint32_t out = (uint32_t)(mask & ((uint64_t(1) << s.low_bits) - 1));
-    int i = s.low_bits;
-    uint64_t rest = s.tile_mask >> s.low_bits << s.low_bits;
-    while (rest) {
-        int b = __builtin_ctzll(rest);
-        if ((mask >> b) & 1) out |= 1u << i;
-        ++i;
-        rest &= rest - 1;
-    }
+    uint32_t out = 0;
+    for (int i = 0; i < s.k; ++i)
+        if ((mask >> s.pos[i]) & 1) out |= 1u << i;
     return out;
 }
 
@@ -98,9 +78,34 @@ uint64_t tile_base(const SweepHost& s, uint64_t tile) {
 }
 
 uint64_t tile_spread(const SweepHost& s, uint32_t j) {
-    const uint32_t lowmask = (1u << s.low_bits) - 1;
-    return (uint64_t)(j & lowmask) | s.spread[0][(j >> s.low_bits) & 63] | s.spread[1][(j >> (s.low_bits + 6)) & 63];
+    uint64_t out = 0;
+    for (int i = 0; i < s.k; ++i)
+        if ((j >> i) & 1) out |= uint64_t(1) << s.pos[i];
+    return out;
 }
+
+// natural index: bit i <-> i-th smallest position of the tile mask
+uint64_t tile_natural_spread(const SweepHost& s, uint32_t nat) {
+    uint64_t out = 0, rest = s.tile_mask;
+    for (int i = 0; rest; ++i, rest &= rest - 1)
+        if ((nat >> i) & 1) out |= uint64_t(1) << __builtin_ctzll(rest);
+    return out;
+}
+
+namespace {
+
+void append_tables(const SweepHost& s, PlanHost& out) {
+    for (uint32_t e = 0; e < (uint32_t)PLAN_TABLE; ++e) {
+        const uint32_t idx = e < 128 ? e : ((e - 128) << 7);  // entries 0..127: index bits 0..6; 128..191: bits 7..12
+        const uint32_t in_tile = idx & ((1u << s.k) - 1u);
+        const uint64_t off = tile_natural_spread(s, in_tile);
+        out.nat_off.push_back(off);
+        out.nat_loc.push_back(compress_to_tile(s, off));
+        out.loc_off.push_back(tile_spread(s, in_tile));
+    }
+}
+
+}  // namespace
 
 int build_plan(const TermView& t, int n_local, int shard, const PlanLimits& lim, PlanHost& out, const char** err) {
     static const char* e_arg = "build_plan: bad geometry";
@@ -174,6 +179,7 @@ int build_plan(const TermView& t, int n_local, int shard, const PlanLimits& lim,
     out.use_tiles = k >= PLAN_MIN_TILE_BITS;
     const int low = std::min(PLAN_LOW_BITS, k);
     const uint64_t lowmask = (uint64_t(1) << low) - 1;
+    const int xcap = k - PLAN_REG_BITS;  // X positions of a tile (lane and row-block bits)
 
     for (auto& kv : by_class) {
         ClassHost cls;
@@ -197,26 +203,25 @@ int build_plan(const TermView& t, int n_local, int shard, const PlanLimits& lim,
         cls.dterm_end = (int64_t)out.d_x.size();
         cls.dgroup_end = (int32_t)out.dg_slot.size();
 
-        // ---- tiled layout: greedy cover of the groups' x_lo by tile masks ----
+        // ---- tiled layout: greedy cover of the groups' x_lo by the X positions of tile masks ----
         cls.sweep_begin = (int32_t)out.sweeps.size();
         if (out.use_tiles) {
             const size_t ng = groups.size();
             std::vector<uint64_t> need(ng);
             std::vector<char> done(ng, 0);
             size_t left = ng;
-            for (size_t g = 0; g < ng; ++g) need[g] = groups[g].x_lo & ~lowmask;
-            const int free_slots = k - low;
+            for (size_t g = 0; g < ng; ++g) need[g] = groups[g].x_lo;
             const double fbase = 8.0;
             double fpow[PLAN_MAX_TILE_BITS + 2];
             for (int m = 0; m <= PLAN_MAX_TILE_BITS + 1; ++m) fpow[m] = std::pow(fbase, -m);
-            // wide groups (more free bits than a tile has) can only be reached through a
-            // non-zero ket_xor; narrow ones are covered first with ket_xor = 0
+            // wide groups (more X bits than a tile has X positions) are reached through a non-zero ket_xor and / or
+            // register rows; narrow ones are covered first with ket_xor = 0 and X masks that avoid the register positions
             while (left > 0) {
                 // seed: virtual all-zero mask while narrow groups remain, else the first wide group
                 uint64_t seed = 0;
                 bool have_narrow = false;
                 for (size_t g = 0; g < ng && !have_narrow; ++g)
-                    if (!done[g] && popc64(need[g]) <= free_slots) have_narrow = true;
+                    if (!done[g] && popc64(need[g]) <= xcap) have_narrow = true;
                 if (!have_narrow) {
                     for (size_t g = 0; g < ng; ++g)
                         if (!done[g]) {
@@ -224,49 +229,83 @@ int build_plan(const TermView& t, int n_local, int shard, const PlanLimits& lim,
                             break;
                         }
                 }
-                uint64_t L = lowmask;
-                if (n_local <= k) {
-                    L = lomask;
-                } else {
-                    for (int step = 0; step < free_slots; ++step) {
-                        const int cap = free_slots - step - 1;  // slots left after this pick
-                        double gain[64];
-                        for (int p = 0; p < 64; ++p) gain[p] = 0.0;
-                        for (size_t g = 0; g < ng; ++g) {
-                            if (done[g]) continue;
-                            uint64_t miss = (need[g] ^ seed) & ~L;
-                            const int m = popc64(miss);
-                            if (m == 0 || m - 1 > cap) continue;
-                            const double d = fpow[m - 1] - (m <= cap ? fpow[m] : 0.0);
-                            while (miss) {
-                                gain[__builtin_ctzll(miss)] += d;
-                                miss &= miss - 1;
-                            }
+                uint64_t Xs = 0;  // X positions
+                for (int step = 0; step < xcap; ++step) {
+                    const int cap = xcap - step - 1;  // slots left after this pick
+                    double gain[64];
+                    for (int p = 0; p < 64; ++p) gain[p] = 0.0;
+                    for (size_t g = 0; g < ng; ++g) {
+                        if (done[g]) continue;
+                        uint64_t miss = (need[g] ^ seed) & ~Xs;
+                        const int m = popc64(miss);
+                        if (m == 0 || m - 1 > cap) continue;
+                        const double d = fpow[m - 1] - (m <= cap ? fpow[m] : 0.0);
+                        while (miss) {
+                            gain[__builtin_ctzll(miss)] += d;
+                            miss &= miss - 1;
                         }
+                    }
+                    // a tile holds the low bits and 4 register positions besides the X positions: keep room for them
+                    int best = -1;
+                    for (int p = 0; p < n_local; ++p)
+                        if (!((Xs >> p) & 1) && (best < 0 || gain[p] > gain[best])) best = p;
+                    if (gain[best] == 0.0) {
+                        // nothing left to gain: pad with the lowest unused positions above what the register rows will take
+                        int spare = 0;
+                        best = -1;
+                        for (int p = 0; p < n_local && best < 0; ++p)
+                            if (!((Xs >> p) & 1) && ++spare > PLAN_REG_BITS) best = p;
+                        if (best < 0) break;
+                    }
+                    Xs |= uint64_t(1) << best;
+                }
+                // register positions: the low bits the X positions left out, then the free positions on which the fewest of the
+                // groups this sweep will take carry Z bits (no Z bit on the register rows = one weight for the 16 rows)
+                uint64_t Rm = lowmask & ~Xs;
+                {
+                    double zcost[64];
+                    for (int p = 0; p < 64; ++p) zcost[p] = 0.0;
+                    for (size_t g = 0; g < ng; ++g) {
+                        if (done[g] || ((need[g] ^ seed) & ~Xs)) continue;
+                        const Group& gr = groups[g];
+                        uint64_t zany = 0, zdiff = 0;
+                        for (int64_t i = gr.tb; i < gr.tb + gr.nt; ++i) {
+                            zany |= recs[i].z;
+                            zdiff |= recs[i].z ^ recs[gr.tb].z;
+                        }
+                        for (uint64_t m = zany & lomask & ~Xs; m; m &= m - 1) zcost[__builtin_ctzll(m)] += 1.0;
+                        for (uint64_t m = zdiff & lomask & ~Xs; m; m &= m - 1) zcost[__builtin_ctzll(m)] += 3.0;  // several runs
+                    }
+                    while (popc64(Rm) < PLAN_REG_BITS) {
                         int best = -1;
-                        for (int p = low; p < n_local; ++p)
-                            if (!((L >> p) & 1) && (best < 0 || gain[p] > gain[best])) best = p;
-                        L |= uint64_t(1) << best;
+                        for (int p = 0; p < n_local; ++p)
+                            if (!(((Xs | Rm) >> p) & 1) && (best < 0 || zcost[p] < zcost[best])) best = p;
+                        if (best < 0) break;
+                        Rm |= uint64_t(1) << best;
                     }
                 }
+                for (int p = 0; p < n_local && popc64(Xs | Rm) < k; ++p)  // early exit of the pick loop: fill the tile
+                    if (!(((Xs | Rm) >> p) & 1)) Xs |= uint64_t(1) << p;
+                const uint64_t L = Xs | Rm;
                 const uint64_t kxor = seed & ~L;
                 SweepHost s;
                 s.cls = ci;
                 s.k = k;
-                s.low_bits = low;
                 s.tile_mask = L;
                 s.ket_xor = kxor;
-                finish_sweep_geometry(s, n_local);
-                // take coverable groups in order until the staging capacity is reached
+                // take coverable groups in order until the staging capacity is reached.  A narrow group that touches a register
+                // position waits for a sweep whose X positions hold all its bits (first pass); wide ones have no such sweep.
                 std::vector<size_t> take;
                 int64_t nterms = 0;
-                for (size_t g = 0; g < ng; ++g) {
-                    if (done[g] || ((need[g] & ~L) != kxor)) continue;
-                    const int nt_padded = (groups[g].nt + 1) & ~1;  // staged term lists are padded to an even length
-                    if ((int)take.size() >= lim.max_groups || nterms + nt_padded > lim.max_terms) break;
-                    take.push_back(g);
-                    nterms += nt_padded;
-                }
+                for (int pass = 0; pass < 2 && take.empty(); ++pass)
+                    for (size_t g = 0; g < ng; ++g) {
+                        if (done[g] || ((need[g] & ~L) != kxor)) continue;
+                        if (pass == 0 && (need[g] & Rm) && popc64(need[g]) <= xcap) continue;
+                        const int nt_padded = (groups[g].nt + 1) & ~1;  // staged term lists are padded to an even length
+                        if ((int)take.size() >= lim.max_groups || nterms + nt_padded > lim.max_terms) break;
+                        take.push_back(g);
+                        nterms += nt_padded;
+                    }
                 // classify coefficients
                 bool cplx = false;
                 std::vector<char> imag(take.size(), 0);
@@ -285,6 +324,50 @@ int build_plan(const TermView& t, int n_local, int shard, const PlanLimits& lim,
                         cplx = true;
                 }
                 s.complex_w = cplx;
+                // tile-local bit order: register rows, then lanes (the low bits among the X positions first: consecutive
+                // amplitudes of a staged segment then differ in the lowest lane bits), then row blocks.  The row-block
+                // positions are picked to hit as many Hermitian groups as possible: those are visited on half the row blocks.
+                {
+                    std::vector<int> rows, lanes, ublk, cand;
+                    for (int p = 0; p < n_local; ++p) {
+                        if ((Rm >> p) & 1) rows.push_back(p);
+                        if (((Xs & lowmask) >> p) & 1) lanes.push_back(p);
+                        if (((Xs & ~lowmask) >> p) & 1) cand.push_back(p);
+                    }
+                    const int nu = k - PLAN_U_SHIFT;
+                    std::vector<char> hit(take.size(), 0);
+                    for (size_t a = 0; a < take.size(); ++a) {
+                        const Group& g = groups[take[a]];
+                        bool eligible = !cplx && !imag[a] && kxor == 0;
+                        for (int64_t i = g.tb; i < g.tb + g.nt && eligible; ++i)
+                            if (!recs[i].herm) eligible = false;
+                        if (!eligible) hit[a] = 1;  // never half-visited: not worth a row-block position
+                    }
+                    for (int iu = 0; iu < nu; ++iu) {
+                        size_t best = 0;
+                        double best_w = -1.0;
+                        for (size_t c = 0; c < cand.size(); ++c) {
+                            double w = 0.0;
+                            for (size_t a = 0; a < take.size(); ++a)
+                                if (!hit[a] && ((groups[take[a]].x_lo >> cand[c]) & 1)) w += 48.0 + 6.0 * groups[take[a]].nt;
+                            if (w > best_w) {
+                                best_w = w;
+                                best = c;
+                            }
+                        }
+                        for (size_t a = 0; a < take.size(); ++a)
+                            if ((groups[take[a]].x_lo >> cand[best]) & 1) hit[a] = 1;
+                        ublk.push_back(cand[best]);
+                        cand.erase(cand.begin() + best);
+                    }
+                    std::sort(ublk.begin(), ublk.end());
+                    for (int p : cand) lanes.push_back(p);
+                    int i = 0;
+                    for (int p : rows) s.pos[i++] = (uint8_t)p;
+                    for (int p : lanes) s.pos[i++] = (uint8_t)p;
+                    for (int p : ublk) s.pos[i++] = (uint8_t)p;
+                }
+                finish_sweep_geometry(s, n_local);
                 s.group_begin = (int32_t)(out.g_hdr.size() / 2);
                 s.term_begin = (int64_t)out.t_zl.size();
                 s.range_begin = (int32_t)(out.r_desc.size() / 2);
@@ -314,15 +397,16 @@ int build_plan(const TermView& t, int n_local, int shard, const PlanLimits& lim,
                     }
                     gi.skipbit = 0;
                     gi.pol = 0;
-                    if (hermitian && !cplx && !gi.imag && kxor == 0 && (gi.xl >> PLAN_SKIP_MIN_BIT) != 0) {
+                    if (hermitian && !cplx && !gi.imag && kxor == 0 && (gi.xl >> PLAN_U_SHIFT) != 0) {
                         gi.skipbit = 31 - __builtin_clz(gi.xl);
-                        // the rows with skip bit == pol do the work of this group: keep the two halves of every bit level
+                        // the rows with skip bit == pol do the work of this group: keep the two halves of every bit level equal
                         const double cost = 48.0 + 6.0 * g.nt;
                         gi.pol = pol_load[gi.skipbit][1] < pol_load[gi.skipbit][0] ? 1 : 0;
                         pol_load[gi.skipbit][gi.pol] += cost;
                     }
                     for (int64_t i = g.tb; i < g.tb + g.nt; ++i) gi.order.push_back(i);
-                    gi.kind = fast ? KIND_FAST : KIND_RUNS;
+                    const bool xrow = (gi.xl & regmask) != 0;
+                    gi.kind = (fast && !xrow) ? KIND_FAST : (KIND_RUNS | (xrow ? KIND_XROW : 0));
                     if (!fast) std::stable_sort(gi.order.begin(), gi.order.end(), [&](int64_t p, int64_t q) { return zreg_of(p) < zreg_of(q); });
                 }
                 std::vector<size_t> ord(take.size());
@@ -364,12 +448,13 @@ int build_plan(const TermView& t, int n_local, int shard, const PlanLimits& lim,
                         out.t_cim.push_back(0.0);
                         ++nt_emit;
                     }
-                    out.g_hdr.push_back(tile_word_of(gi.xl) | ((uint32_t)nt_emit << HDR_NT_SHIFT) | (gi.imag ? HDR_IMAG : 0u));
+                    out.g_hdr.push_back(gi.xl | ((uint32_t)nt_emit << HDR_NT_SHIFT) | (gi.imag ? HDR_IMAG : 0u));
                     out.g_hdr.push_back(0u);
                     out.g_slot.push_back(g.slot);
                     done[gi.gi] = 1;
                     --left;
                 }
+                append_tables(s, out);
                 s.range_end = (int32_t)(out.r_desc.size() / 2);
                 s.group_end = (int32_t)(out.g_hdr.size() / 2);
                 s.term_end = (int64_t)out.t_zl.size();

@@ -4,10 +4,12 @@
 // A *group* is the set of terms of one operator slot that share an X mask.  Groups whose X mask
 // has high part x_hi (the bits above n_local) form *class* x_hi: they read the ket shard of rank
 // shard^x_hi.  Inside a class the groups are covered by *sweeps*: a sweep fixes a set L of k
-// shard-local bit positions (the low ``low_bits`` positions plus k-low_bits free ones); every
-// group of the sweep has x_lo = ket_xor + (bits inside L) with one ket_xor outside L, so a CTA that stages the 2^k amplitudes {base | spread(j)}
-// of one *tile* in shared memory finds every XOR partner in that tile.  One sweep = one kernel
-// launch = one pass over the shard in HBM, evaluating all its groups.
+// shard-local bit positions (the *tile mask*): 4 *register positions* that (almost) no X mask of the sweep touches, and k-4
+// *X positions* (5 lane bits, up to 4 row-block bits).  Every group of the sweep has x_lo = ket_xor + (bits inside L) with one
+// ket_xor outside L, so a CTA that stages the 2^k amplitudes {base | spread(j)} of one *tile* in shared memory finds every
+// XOR partner in that tile.  One sweep = one kernel launch = one pass over the shard in HBM, evaluating all its groups.
+// Tile-local index j: bits 0..3 = register rows (16 amplitudes a thread keeps in registers), bits 4..8 = lane, bits 9.. =
+// row block (warp).  The 3 lowest shard bits are always in the tile (128 B contiguous segments in HBM).
 #pragma once
 
 #include <cstdint>
@@ -26,17 +28,16 @@ struct TermView {
     const double* constant = nullptr;  // 2*n_slots
 };
 
-constexpr int PLAN_MAX_TILE_BITS = 13;  // the header keeps 13 bits of tile-local X mask
-constexpr int PLAN_LOW_BITS = 3;        // 8 amplitudes = 128 B (c128) contiguous per gather segment
+constexpr int PLAN_MAX_TILE_BITS = 13;  // 2^13 complex128 amplitudes = 128 KB of shared memory
+constexpr int PLAN_LOW_BITS = 3;        // 8 amplitudes = 128 B (c128) contiguous per gather segment: always inside the tile
 constexpr int PLAN_REG_BITS = 4;        // tile-local bits [0, 4) index the 16 rows a thread keeps in registers
 constexpr int PLAN_U_SHIFT = PLAN_REG_BITS + 5;  // tile-local bits >= 9 are warp-uniform (row-block index = warp index)
 constexpr int PLAN_MIN_TILE_BITS = PLAN_U_SHIFT; // one full warp row block; below this the direct kernel is used
-constexpr int PLAN_SKIP_MIN_BIT = PLAN_REG_BITS + 3;  // a skip bit on lane bit >= 3 still idles whole quarter warps (128-bit accesses)
 constexpr int PLAN_MAX_RUNS = 24;
-static_assert(PLAN_REG_BITS >= PLAN_LOW_BITS, "register rows contain the contiguous low amplitudes");
+constexpr int PLAN_TABLE = 192;         // per-sweep lookup tables: 128 entries for index bits 0..6, 64 for bits 7..12
 
 // group header word a
-constexpr uint32_t HDR_XL_MASK = 0x1fffu;   // bits 0..12: tile-local X mask in shared-memory word form, tile_word_of(xl)
+constexpr uint32_t HDR_XL_MASK = 0x1fffu;   // bits 0..12: tile-local X mask (bits 0..3 = register rows, 4..12 = thread)
 constexpr int HDR_NT_SHIFT = 13;            // bits 13..24: number of staged terms (<= 4095)
 constexpr uint32_t HDR_NT_MASK = 0xfffu;
 constexpr uint32_t HDR_IMAG = 1u << 25;     // gather coefficients purely imaginary (stored in t_cre)
@@ -48,20 +49,23 @@ constexpr uint32_t TZ_HI_MASK = ((1u << PLAN_MAX_TILE_BITS) - 1u) & ~((1u << PLA
 constexpr int TZ_V_SHIFT = 16, TZ_RUN_SHIFT = 20;
 
 // A sweep's groups are ordered into *ranges* of equal (skip bit, polarity, kind):
-//   skip bit: tile-local index (>= PLAN_SKIP_MIN_BIT) of the top X bit of a Hermitian group with real gather coefficients, 0 if
-//             none.  <psi|G|psi> on one tile equals 2 Re over the rows whose skip bit equals the range's polarity, so the other
-//             rows (whole warps for bits >= PLAN_U_SHIFT, whole quarter warps below) skip the range.  The planner balances the
-//             two polarities of every skip bit so that all row blocks carry the same work;
-//   kind:     how W(row) = sum_t c_t (-1)^{|z_t & row|} is formed for the thread's 16 register rows.
+//   skip bit: tile-local index (>= PLAN_U_SHIFT) of the top X bit of a Hermitian group with real gather coefficients, 0 if
+//             none.  <psi|G|psi> on one tile equals 2 Re over the rows whose skip bit equals the range's polarity, so the row
+//             blocks (warps) of the other polarity skip the range.  The planner balances the two polarities of every skip bit
+//             so that all row blocks carry the same work;
+//   kind:     how W(row) = sum_t c_t (-1)^{|z_t & row|} is formed for the thread's 16 register rows, and where the partner rows are.
 enum { KIND_FAST = 0,  // no z bit on the register rows: W is the same for the 16 rows; term list padded to an even length
-       KIND_RUNS = 1   // terms sorted by their register-row z bits v: one signed sum S per run, <.> folded with (-1)^{v.r}
+       KIND_RUNS = 1,  // terms sorted by their register-row z bits v: one signed sum S per run, <.> folded with (-1)^{v.r}
+       KIND_XROW = 2   // flag: the X mask touches register rows (partner row = row ^ xr); combined with KIND_RUNS
 };
 // range descriptor: word 0 = first group | (one past the last group) << 16 (sweep-local);
 //                   word 1 = first term (sweep-local) | kind << 16 | polarity << 18 | skip bit << 24
 constexpr int RNG_KIND_SHIFT = 16, RNG_POL_SHIFT = 18, RNG_SKIP_SHIFT = 24;
 
-// shared-memory word of tile-local index j (an involution, linear over GF(2)): see sweep.cu
-inline uint32_t tile_word_of(uint32_t j) { return j ^ ((j >> PLAN_REG_BITS) & 7u); }
+// shared-memory word (16 B units for complex128) of tile-local index j: row-major planes, one plane per register row, padded to
+// an odd length so that the 8 rows a quarter warp stages land on 8 distinct bank groups
+constexpr uint32_t PLAN_PLANE = 513;
+inline uint32_t tile_word_of(uint32_t j) { return (j & 15u) * PLAN_PLANE + (j >> PLAN_REG_BITS); }
 
 struct PlanLimits {
     int tile_bits = 13;
@@ -72,13 +76,12 @@ struct PlanLimits {
 struct SweepHost {
     int cls = 0;            // index into PlanHost::classes
     int k = 0;              // tile bits
-    int low_bits = 0;       // identity-mapped low bits
     uint64_t tile_mask = 0; // L
     uint64_t ket_xor = 0;   // shard-local bits outside L shared by every X mask of the sweep: ket tile = base ^ ket_xor
+    uint8_t pos[PLAN_MAX_TILE_BITS] = {0};  // tile-local bit i <-> shard position pos[i]
     int n_runs = 0;         // runs of the outer mask (shard bits outside L), LSB first
     uint8_t run_pos[PLAN_MAX_RUNS] = {0};
     uint8_t run_len[PLAN_MAX_RUNS] = {0};
-    uint64_t spread[2][64] = {{0}};  // tile-local bits [low, low+6) and [low+6, low+12) -> shard positions
     int64_t n_tiles = 0;
     int32_t group_begin = 0, group_end = 0;
     int64_t term_begin = 0, term_end = 0;
@@ -103,6 +106,10 @@ struct PlanHost {
     std::vector<uint32_t> g_hdr;
     std::vector<int32_t> g_slot;
     std::vector<uint32_t> r_desc;  // two words per range
+    // per sweep, PLAN_TABLE entries each: *natural* index (bit i <-> i-th smallest position of L; what the coalesced staging loop
+    // enumerates) -> shard offset and -> tile-local index; tile-local index -> shard offset
+    std::vector<uint64_t> nat_off, loc_off;
+    std::vector<uint32_t> nat_loc;
     std::vector<uint32_t> t_zl;    // staged term word, see the TZ_* constants
     std::vector<uint64_t> t_zo;    // shard-local z bits outside the tile
     std::vector<double> t_cre, t_cim;  // gather-form coefficients, rank sign folded; imag groups keep Im in t_cre
@@ -121,5 +128,6 @@ uint32_t compress_to_tile(const SweepHost& s, uint64_t mask);
 // shard position of tile-local index j for tile number `tile`
 uint64_t tile_base(const SweepHost& s, uint64_t tile);
 uint64_t tile_spread(const SweepHost& s, uint32_t j);
+uint64_t tile_natural_spread(const SweepHost& s, uint32_t nat);
 
 }  // namespace qfe

@@ -28,9 +28,10 @@ constexpr int NT = 512;           // threads per CTA of the tile kernel: one war
 constexpr int NW = NT / 32;
 constexpr int RB = PLAN_REG_BITS; // register-blocked rows per thread: R = 16 (tile-local bits 0..3)
 constexpr int R = 1 << RB;
-// shared-memory word of tile-local index j is j ^ ((j >> 4) & 7): the 16 rows of a thread sit in two 128 B lines, rotated by
-// the low lane bits so that a quarter warp's 128-bit accesses hit 8 distinct bank groups.  The map is linear over GF(2), so
-// the partner j ^ x of row j lives at word(j) ^ word(x): one XOR per group, the X bits on the register rows included.
+// shared-memory word of tile-local index j is (j & 15) * 513 + (j >> 4): one plane of 512 words per register row, padded to an
+// odd length.  Thread t owns word t of every plane; the partner of row r for X mask (xt, xr = 0) is word t ^ xt of the same plane,
+// i.e. 16 loads at [register + immediate]; a warp reads a permutation of 32 consecutive 16 B words (conflict-free), and the 8
+// consecutive amplitudes a quarter warp stages land on 8 different bank groups (different planes, or consecutive words).
 static_assert(PLAN_MIN_TILE_BITS == 5 + RB, "a tile must hold at least one full warp row block");
 static_assert(PLAN_U_SHIFT == 5 + RB, "warp-uniform tile bits start above the lane and register bits");
 static_assert((1 << (PLAN_MAX_TILE_BITS - 5 - RB)) == NW, "one warp per row block of the largest tile");
@@ -64,24 +65,29 @@ struct SweepArgs {
     const double* t_cre;
     const double* t_cim;
     int n_groups, n_terms, n_ranges;
-    int k, low_bits, n_runs;
+    const uint64_t* nat_off;  // PLAN_TABLE entries each, see plan_host.h
+    const uint64_t* loc_off;
+    const uint32_t* nat_loc;
+    int k, n_runs;
     int same_tile, accumulate;
     unsigned long long n_tiles;
     unsigned long long ket_xor;
     uint8_t run_pos[PLAN_MAX_RUNS];
     uint8_t run_len[PLAN_MAX_RUNS];
-    uint64_t spread[128];
 };
 
 // Fixed shared-memory map (bytes), sized for the largest sweep (2^13 complex128 amplitudes, 2048 complex-coefficient terms):
 // constant offsets let every access be [register + immediate] with nothing to recompute inside the group loop.
-constexpr uint32_t SM_TILE = 0;                         // 128 KB tile
-constexpr uint32_t SM_REC = 131072;                     // 64 KB staged terms (2048 x 32 B)
+constexpr uint32_t PLANE = PLAN_PLANE;                  // words per register-row plane
+constexpr uint32_t SM_TILE = 0;                         // 16 planes x 513 x 16 B
+constexpr uint32_t SM_REC = R * PLANE * 16;             // 64 KB staged terms (2048 x 32 B)
 constexpr uint32_t SM_ACC = SM_REC + 32768;             // BATCH only (<= 1024 terms staged): per-warp per-group accumulators, 32 KB
 constexpr uint32_t SM_HDR = SM_REC + 65536;             // 4 KB group headers (512 x 8 B)
 constexpr uint32_t SM_RNG = SM_HDR + 4096;              // 2 KB range descriptors (256 x 8 B)
-constexpr uint32_t SM_SPREAD = SM_RNG + 2048;           // 1 KB tile-index -> shard-position tables
-constexpr uint32_t SM_RED = SM_SPREAD + 1024;           // block reduction scratch
+constexpr uint32_t SM_NATOFF = SM_RNG + 2048;           // index tables of the sweep (plan_host.h)
+constexpr uint32_t SM_LOCOFF = SM_NATOFF + PLAN_TABLE * 8;
+constexpr uint32_t SM_NATLOC = SM_LOCOFF + PLAN_TABLE * 8;
+constexpr uint32_t SM_RED = SM_NATLOC + PLAN_TABLE * 4; // block reduction scratch
 constexpr uint32_t SM_TOTAL = SM_RED + NW * 16;
 constexpr int SWEEP_MAX_TERMS = 2048, SWEEP_MAX_GROUPS = 512;  // ranges per sweep <= 7 skip levels x 2 polarities x 2 kinds
 constexpr int BATCH_MAX_TERMS = 1024, BATCH_MAX_GROUPS = 128;
@@ -158,7 +164,13 @@ __device__ __forceinline__ void load_rec(const TermRec<float, true>* p, float& c
     zp = raw.z;
 }
 
-__device__ __forceinline__ uint32_t tile_word(uint32_t j) { return j ^ ((j >> RB) & 7u); }
+__device__ __forceinline__ uint32_t tile_word(uint32_t j) { return (j & (uint32_t)(R - 1)) * PLANE + (j >> RB); }
+
+// partner of the thread's row r: word t ^ xt of plane r (pp points at it), or of plane r ^ xr when the X mask touches register rows
+template <bool XROW, typename cplx_t>
+__device__ __forceinline__ cplx_t partner_row(const cplx_t* __restrict__ pp, const uint32_t xr, const int r) {
+    return XROW ? pp[((uint32_t)r ^ xr) * PLANE] : pp[(uint32_t)r * PLANE];
+}
 
 // S = sum_t c_t (-1)^{|z_t & jhi|} over the staged terms [t, te).  jhi only has lane / row-block bits set, so the run fields in the
 // upper half of the term word never reach the popc.  EVEN: te - t is even (KIND_FAST lists are padded): two independent chains.
@@ -231,19 +243,20 @@ __device__ __forceinline__ void times_weight(real_t& sr, real_t& si, const real_
     }
 }
 
-// <own| G |tile> of one group for the thread's 16 rows: sum_r conj(own_r) Wc(r) p_r with p_r the partner of row r at tile word pw ^ r.
+// <own| G |tile> of one group for the thread's 16 rows: sum_r conj(own_r) Wc(r) p_r with p_r the partner of row r.
 template <typename real_t, bool CPLX, int KIND>
-__device__ __forceinline__ void group_value_full(const typename CplxOf<real_t>::type* __restrict__ tile, const TermRec<real_t, CPLX>* __restrict__ s_rec, const uint32_t pw,
+__device__ __forceinline__ void group_value_full(const typename CplxOf<real_t>::type* __restrict__ pp, const uint32_t xr, const TermRec<real_t, CPLX>* __restrict__ s_rec,
                                                  const int tb, const int nt, const bool imag, const uint32_t jhi,
                                                  const typename CplxOf<real_t>::type (&own)[R], real_t& out_re, real_t& out_im) {
     using cplx_t = typename CplxOf<real_t>::type;
+    (void)xr;
     if (KIND == KIND_FAST) {
         real_t Sre, Sim;
         signed_sum<real_t, CPLX, true>(s_rec, tb, tb + nt, jhi, Sre, Sim);
         real_t a0 = (real_t)0, a1 = (real_t)0, b0 = (real_t)0, b1 = (real_t)0;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const cplx_t p = tile[pw ^ (uint32_t)r];
+            const cplx_t p = partner_row<(KIND & KIND_XROW) != 0>(pp, xr, r);
             a0 = fma(own[r].x, p.x, a0);  // Re conj(own) p = a a' + b b'
             a1 = fma(own[r].y, p.y, a1);
             b0 = fma(own[r].x, p.y, b0);  // Im conj(own) p = a b' - b a'
@@ -262,7 +275,7 @@ __device__ __forceinline__ void group_value_full(const typename CplxOf<real_t>::
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const int r = 8 * ch + q;
-                const cplx_t p = tile[pw ^ (uint32_t)r];
+                const cplx_t p = partner_row<(KIND & KIND_XROW) != 0>(pp, xr, r);
                 fr[q] = fma(own[r].x, p.x, own[r].y * p.y);
                 fi[q] = fma(own[r].x, p.y, -own[r].y * p.x);
             }
@@ -298,12 +311,13 @@ __device__ __forceinline__ void process_range(const typename CplxOf<real_t>::typ
                                               const uint2* __restrict__ s_hdr, double2* __restrict__ s_acc_warp, const int g0, const int g1, int tb,
                                               const uint32_t w0, const uint32_t jhi, const bool half,
                                               const typename CplxOf<real_t>::type (&own)[R], real_t (&acc_re)[R], real_t (&acc_im)[R],
-                                              double& e_re, double& e_im, double& e_half) {
+                                              double& e_re, double& e_im) {
     using cplx_t = typename CplxOf<real_t>::type;
 #pragma unroll 1
     for (int g = g0; g < g1; ++g) {
         const uint32_t hdr = s_hdr[g].x;
-        const uint32_t pw = w0 ^ (hdr & HDR_XL_MASK);  // header keeps the X mask already in word form
+        const cplx_t* __restrict__ pp = tile + (w0 ^ ((hdr & HDR_XL_MASK) >> RB));  // partner thread's word of plane 0
+        const uint32_t xr = hdr & (uint32_t)(R - 1);
         const int nt = (int)((hdr >> HDR_NT_SHIFT) & HDR_NT_MASK);
         const bool imag = hdr & HDR_IMAG;
         if (MODE == MODE_EXPECT && half) {
@@ -315,7 +329,7 @@ __device__ __forceinline__ void process_range(const typename CplxOf<real_t>::typ
                 real_t a0 = (real_t)0, a1 = (real_t)0, a2 = (real_t)0, a3 = (real_t)0;  // independent chains keep the FP64 pipe busy
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    const cplx_t p = tile[pw ^ (uint32_t)r];
+                    const cplx_t p = partner_row<(KIND & KIND_XROW) != 0>(pp, xr, r);
                     if (r & 1) {
                         a2 = fma(own[r].x, p.x, a2);
                         a3 = fma(own[r].y, p.y, a3);
@@ -324,12 +338,12 @@ __device__ __forceinline__ void process_range(const typename CplxOf<real_t>::typ
                         a1 = fma(own[r].y, p.y, a1);
                     }
                 }
-                e_half += (double)S * (double)((a0 + a1) + (a2 + a3));
+                e_re = fma((double)(S + S), (double)((a0 + a1) + (a2 + a3)), e_re);  // the pair counts twice
             } else {
                 real_t f[R];
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    const cplx_t p = tile[pw ^ (uint32_t)r];
+                    const cplx_t p = partner_row<(KIND & KIND_XROW) != 0>(pp, xr, r);
                     f[r] = fma(own[r].x, p.x, own[r].y * p.y);
                 }
                 int t = tb;
@@ -345,11 +359,11 @@ __device__ __forceinline__ void process_range(const typename CplxOf<real_t>::typ
                     t += len;
                     tot = fma(S, fold_rows<real_t, R>(f, v), tot);
                 }
-                e_half += (double)tot;
+                e_re += (double)(tot + tot);
             }
         } else if (MODE == MODE_EXPECT || MODE == MODE_BATCH) {
             real_t sr, si;
-            group_value_full<real_t, CPLX, KIND>(tile, s_rec, pw, tb, nt, imag, jhi, own, sr, si);
+            group_value_full<real_t, CPLX, KIND>(pp, xr, s_rec, tb, nt, imag, jhi, own, sr, si);
             if (MODE == MODE_EXPECT) {
                 e_re += (double)sr;
                 e_im += (double)si;
@@ -376,7 +390,7 @@ __device__ __forceinline__ void process_range(const typename CplxOf<real_t>::typ
                 const real_t wi = CPLX ? Sim : (imag ? Sre : (real_t)0);
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    const cplx_t p = tile[pw ^ (uint32_t)r];
+                    const cplx_t p = partner_row<(KIND & KIND_XROW) != 0>(pp, xr, r);
                     if (CPLX) {
                         acc_re[r] += wr * p.x - wi * p.y;
                         acc_im[r] += wr * p.y + wi * p.x;
@@ -434,7 +448,7 @@ __device__ __forceinline__ void process_range(const typename CplxOf<real_t>::typ
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         const int r = 8 * ch + q;
-                        const cplx_t p = tile[pw ^ (uint32_t)r];
+                        const cplx_t p = partner_row<(KIND & KIND_XROW) != 0>(pp, xr, r);
                         if (CPLX) {
                             acc_re[r] += W[q] * p.x - Wi[q] * p.y;
                             acc_im[r] += W[q] * p.y + Wi[q] * p.x;
@@ -465,7 +479,9 @@ __global__ void __launch_bounds__(NT, 1) tile_sweep_kernel(const __grid_constant
     rec_t* s_rec = reinterpret_cast<rec_t*>(smem + SM_REC);
     uint2* s_hdr = reinterpret_cast<uint2*>(smem + SM_HDR);
     uint2* s_rng = reinterpret_cast<uint2*>(smem + SM_RNG);
-    uint64_t* s_spread = reinterpret_cast<uint64_t*>(smem + SM_SPREAD);
+    uint64_t* s_nat_off = reinterpret_cast<uint64_t*>(smem + SM_NATOFF);
+    uint64_t* s_loc_off = reinterpret_cast<uint64_t*>(smem + SM_LOCOFF);
+    uint32_t* s_nat_loc = reinterpret_cast<uint32_t*>(smem + SM_NATLOC);
     double2* s_acc = reinterpret_cast<double2*>(smem + SM_ACC);
     double2* s_red = reinterpret_cast<double2*>(smem + SM_RED);
 
@@ -477,18 +493,20 @@ __global__ void __launch_bounds__(NT, 1) tile_sweep_kernel(const __grid_constant
     // ---- once per CTA: tile-independent tables ------------------------------------------------
     for (int g = tid; g < nG; g += NT) s_hdr[g] = make_uint2(a.g_hdr[2 * g], a.g_hdr[2 * g + 1]);
     for (int g = tid; g < nR; g += NT) s_rng[g] = make_uint2(a.r_desc[2 * g], a.r_desc[2 * g + 1]);
-    for (int i = tid; i < 128; i += NT) s_spread[i] = a.spread[i];
+    for (int i = tid; i < PLAN_TABLE; i += NT) {
+        s_nat_off[i] = a.nat_off[i];
+        s_loc_off[i] = a.loc_off[i];
+        s_nat_loc[i] = a.nat_loc[i];
+    }
     for (int t = tid; t < nT; t += NT) s_rec[t].zp = a.t_zl[t];
     if (MODE == MODE_BATCH)
         for (int i = tid; i < NW * nG; i += NT) s_acc[i] = make_double2(0.0, 0.0);
 
-    const int low = a.low_bits;
-    const uint32_t lowmask = (1u << low) - 1u;
-    // one warp per row block of 512 amplitudes: thread tid owns the 16 rows jhi | r
+    // one warp per row block of 512 amplitudes: thread tid owns the 16 rows jhi | r = word tid of the 16 planes
     const bool active = warp < (1 << (k - 5 - RB));
     const uint32_t jhi = (uint32_t)tid << RB;  // tile-local index of row 0 (lane and row-block bits)
-    const uint32_t w0 = tile_word(jhi);        // its shared-memory word; row r is at w0 ^ r
-    double e_re = 0.0, e_im = 0.0, e_half = 0.0;
+    const uint32_t w0 = (uint32_t)tid;
+    double e_re = 0.0, e_im = 0.0;
 
     for (unsigned long long tile_id = blockIdx.x; tile_id < a.n_tiles; tile_id += gridDim.x) {
         // shard position of the tile: deposit the tile number into the bits outside the tile mask
@@ -504,21 +522,26 @@ __global__ void __launch_bounds__(NT, 1) tile_sweep_kernel(const __grid_constant
         __syncthreads();  // previous tile fully consumed (also orders the one-time tables)
         {
             const uint64_t kbase = base ^ a.ket_xor;
-            // 2^k / NT amplitudes per thread (a power of two); full tiles keep 8 independent 128-bit loads in flight per step
+            // the tile is enumerated in natural order (consecutive threads = consecutive amplitudes of a 128 B segment) and
+            // scattered to its tile-local words; full tiles keep 8 independent 128-bit loads in flight per step
             if (tile_amps >= 8 * NT) {
                 for (uint32_t i0 = tid; i0 < tile_amps; i0 += 8 * NT) {
                     cplx_t v[8];
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
                         const uint32_t idx = i0 + u * NT;
-                        v[u] = ld_stream(ket + (kbase | (idx & lowmask) | s_spread[(idx >> low) & 63] | s_spread[64 + ((idx >> (low + 6)) & 63)]));
+                        v[u] = ld_stream(ket + (kbase | s_nat_off[idx & 127] | s_nat_off[128 + (idx >> 7)]));
                     }
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) tile[tile_word(i0 + u * NT)] = v[u];
+                    for (int u = 0; u < 8; ++u) {
+                        const uint32_t idx = i0 + u * NT;
+                        tile[tile_word(s_nat_loc[idx & 127] | s_nat_loc[128 + (idx >> 7)])] = v[u];
+                    }
                 }
             } else {
                 for (uint32_t idx = tid; idx < tile_amps; idx += NT)
-                    tile[tile_word(idx)] = ld_stream(ket + (kbase | (idx & lowmask) | s_spread[(idx >> low) & 63] | s_spread[64 + ((idx >> (low + 6)) & 63)]));
+                    tile[tile_word(s_nat_loc[idx & 127] | s_nat_loc[128 + (idx >> 7)])] =
+                        ld_stream(ket + (kbase | s_nat_off[idx & 127] | s_nat_off[128 + (idx >> 7)]));
             }
             // coefficients with the sign of the z bits outside the tile (constant over the tile)
             for (int t = tid; t < nT; t += NT) {
@@ -543,10 +566,10 @@ __global__ void __launch_bounds__(NT, 1) tile_sweep_kernel(const __grid_constant
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     if (a.same_tile) {
-                        own[r] = tile[w0 ^ (uint32_t)r];
+                        own[r] = tile[(uint32_t)r * PLANE + w0];
                     } else {
                         const uint32_t j = jhi | (uint32_t)r;
-                        own[r] = bra[base | (j & lowmask) | s_spread[(j >> low) & 63] | s_spread[64 + ((j >> (low + 6)) & 63)]];
+                        own[r] = bra[base | s_loc_off[j & 127] | s_loc_off[128 + (j >> 7)]];
                     }
                 }
             }
@@ -558,21 +581,23 @@ __global__ void __launch_bounds__(NT, 1) tile_sweep_kernel(const __grid_constant
                 bool half = false;
                 if (MODE == MODE_EXPECT) {
                     half = a.same_tile && skipbit != 0;
-                    // the rows with the other polarity are the partners of these pairs (whole warps for row-block bits, whole
-                    // quarter warps for the two top lane bits)
+                    // the row blocks (warps) of the other polarity hold the partners of these pairs
                     if (half && (((jhi >> skipbit) ^ (d.y >> RNG_POL_SHIFT)) & 1u)) continue;
                 }
                 const int g0 = (int)(d.x & 0xffffu), g1 = (int)(d.x >> 16), t0 = (int)(d.y & 0xffffu);
-                if (((d.y >> RNG_KIND_SHIFT) & 3u) == KIND_FAST)
-                    process_range<real_t, CPLX, MODE, KIND_FAST>(tile, s_rec, s_hdr, s_acc_warp, g0, g1, t0, w0, jhi, half, own, acc_re, acc_im, e_re, e_im, e_half);
+                const uint32_t kind = (d.y >> RNG_KIND_SHIFT) & 3u;
+                if (kind == KIND_FAST)
+                    process_range<real_t, CPLX, MODE, KIND_FAST>(tile, s_rec, s_hdr, s_acc_warp, g0, g1, t0, w0, jhi, half, own, acc_re, acc_im, e_re, e_im);
+                else if (kind == KIND_RUNS)
+                    process_range<real_t, CPLX, MODE, KIND_RUNS>(tile, s_rec, s_hdr, s_acc_warp, g0, g1, t0, w0, jhi, half, own, acc_re, acc_im, e_re, e_im);
                 else
-                    process_range<real_t, CPLX, MODE, KIND_RUNS>(tile, s_rec, s_hdr, s_acc_warp, g0, g1, t0, w0, jhi, half, own, acc_re, acc_im, e_re, e_im, e_half);
+                    process_range<real_t, CPLX, MODE, KIND_RUNS | KIND_XROW>(tile, s_rec, s_hdr, s_acc_warp, g0, g1, t0, w0, jhi, half, own, acc_re, acc_im, e_re, e_im);
             }
             if (MODE == MODE_APPLY) {
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     const uint32_t j = jhi | (uint32_t)r;
-                    const uint64_t gidx = base | (j & lowmask) | s_spread[(j >> low) & 63] | s_spread[64 + ((j >> (low + 6)) & 63)];
+                    const uint64_t gidx = base | s_loc_off[j & 127] | s_loc_off[128 + (j >> 7)];
                     cplx_t y;
                     if (a.accumulate) {
                         y = yout[gidx];
@@ -589,7 +614,7 @@ __global__ void __launch_bounds__(NT, 1) tile_sweep_kernel(const __grid_constant
     }
 
     if (MODE == MODE_EXPECT) {
-        double2 tot = block_reduce_sum(make_double2(e_re + 2.0 * e_half, e_im), s_red);
+        double2 tot = block_reduce_sum(make_double2(e_re, e_im), s_red);
         if (tid == 0) a.partials[blockIdx.x] = tot;
     } else if (MODE == MODE_BATCH) {
         __syncthreads();
@@ -708,7 +733,7 @@ struct qfe_plan {
     bool batch = false;
     bool force_direct = false;
     int device = 0;
-    DevBuf g_hdr, r_desc, t_zl, t_zo, t_cre, t_cim, d_x, d_z, d_cre, d_cim, dg_begin;
+    DevBuf g_hdr, r_desc, t_zl, t_zo, t_cre, t_cim, d_x, d_z, d_cre, d_cim, dg_begin, nat_off, loc_off, nat_loc;
 };
 
 namespace qfe {
@@ -770,14 +795,15 @@ static void fill_sweep_args(const qfe_plan* p, const SweepHost& s, SweepArgs& a)
     a.n_groups = s.group_end - s.group_begin;
     a.n_terms = (int)(s.term_end - s.term_begin);
     a.k = s.k;
-    a.low_bits = s.low_bits;
     a.n_runs = s.n_runs;
     a.n_tiles = (unsigned long long)s.n_tiles;
     a.ket_xor = s.ket_xor;
     memcpy(a.run_pos, s.run_pos, sizeof(a.run_pos));
     memcpy(a.run_len, s.run_len, sizeof(a.run_len));
-    memcpy(a.spread, s.spread[0], 64 * sizeof(uint64_t));
-    memcpy(a.spread + 64, s.spread[1], 64 * sizeof(uint64_t));
+    const size_t si = (size_t)(&s - p->h.sweeps.data());
+    a.nat_off = p->nat_off.as<uint64_t>() + si * PLAN_TABLE;
+    a.loc_off = p->loc_off.as<uint64_t>() + si * PLAN_TABLE;
+    a.nat_loc = p->nat_loc.as<uint32_t>() + si * PLAN_TABLE;
 }
 
 // Runs every sweep of one class in EXPECT or BATCH mode and leaves per-range values in host_vals
@@ -918,7 +944,8 @@ int qfe_plan_create(qfe_ctx* ctx, const qfe_terms* t, int n_local, int shard, in
     if ((rc = upload(p->g_hdr, p->h.g_hdr, s)) || (rc = upload(p->r_desc, p->h.r_desc, s)) || (rc = upload(p->t_zl, p->h.t_zl, s)) || (rc = upload(p->t_zo, p->h.t_zo, s)) ||
         (rc = upload(p->t_cre, p->h.t_cre, s)) || (rc = upload(p->t_cim, p->h.t_cim, s)) || (rc = upload(p->d_x, p->h.d_x, s)) ||
         (rc = upload(p->d_z, p->h.d_z, s)) || (rc = upload(p->d_cre, p->h.d_cre, s)) || (rc = upload(p->d_cim, p->h.d_cim, s)) ||
-        (rc = upload(p->dg_begin, p->h.dg_begin, s))) {
+        (rc = upload(p->dg_begin, p->h.dg_begin, s)) || (rc = upload(p->nat_off, p->h.nat_off, s)) || (rc = upload(p->loc_off, p->h.loc_off, s)) ||
+        (rc = upload(p->nat_loc, p->h.nat_loc, s))) {
         delete p;
         return rc;
     }

@@ -54,6 +54,23 @@ extern "C" int plan_emul_run(int n, int64_t T, const uint64_t* x, const uint64_t
             stats[1] += s.group_end - s.group_begin;
             stats[2] += s.term_end - s.term_begin;
             const uint32_t tile_amps = 1u << s.k;
+            // staging tables: natural index (coalesced order) -> shard offset / tile-local index, tile-local index -> shard offset
+            if (p.nat_off.size() != p.sweeps.size() * PLAN_TABLE || p.nat_loc.size() != p.nat_off.size() || p.loc_off.size() != p.nat_off.size()) return 22;
+            {
+                const uint64_t* no = p.nat_off.data() + (size_t)si * PLAN_TABLE;
+                const uint32_t* nl = p.nat_loc.data() + (size_t)si * PLAN_TABLE;
+                const uint64_t* lo = p.loc_off.data() + (size_t)si * PLAN_TABLE;
+                if ((s.tile_mask & 7u) != 7u) return 23;  // 128 B segments: the three low bits are in every tile
+                std::vector<char> seen_loc(tile_amps, 0);
+                for (uint32_t nat = 0; nat < tile_amps; ++nat) {
+                    const uint64_t off = no[nat & 127] | no[128 + (nat >> 7)];
+                    const uint32_t loc = nl[nat & 127] | nl[128 + (nat >> 7)];
+                    if ((off & 7u) != (nat & 7u) || (off & ~s.tile_mask)) return 24;
+                    if (loc >= tile_amps || seen_loc[loc]) return 25;
+                    seen_loc[loc] = 1;
+                    if ((lo[loc & 127] | lo[128 + (loc >> 7)]) != off || tile_spread(s, loc) != off) return 26;
+                }
+            }
             std::vector<cplx> tile(tile_amps);
             std::vector<char> seen;
             if (si == cls.sweep_begin) seen.assign(size_t(1) << n_local, 0);
@@ -84,16 +101,17 @@ extern "C" int plan_emul_run(int n, int64_t T, const uint64_t* x, const uint64_t
                         const uint32_t pol = (d1 >> RNG_POL_SHIFT) & 1u;
                         const uint32_t skipbit = d1 >> RNG_SKIP_SHIFT;
                         if (g0 != g_expect || (int64_t)(d1 & 0xffffu) != t_expect || g1 <= g0) return 10;  // ranges tile the sweep's groups in order
-                        if (skipbit && (skipbit < (uint32_t)PLAN_SKIP_MIN_BIT || skipbit >= (uint32_t)s.k || s.ket_xor != 0)) return 11;
-                        if (kind != KIND_FAST && kind != KIND_RUNS) return 12;
+                        if (skipbit && (skipbit < (uint32_t)PLAN_U_SHIFT || skipbit >= (uint32_t)s.k || s.ket_xor != 0)) return 11;
+                        if (kind != KIND_FAST && kind != KIND_RUNS && kind != (KIND_RUNS | KIND_XROW)) return 12;
                         int64_t tb = s.term_begin + t_expect;
                         for (int gl = g0; gl < g1; ++gl) {
                             const int g = s.group_begin + gl;
                             const uint32_t ha = p.g_hdr[2 * g];
-                            const uint32_t xl = tile_word_of(ha & HDR_XL_MASK);  // the header keeps the X mask in word form (an involution)
+                            const uint32_t xl = ha & HDR_XL_MASK;
                             const int nt = (int)((ha >> HDR_NT_SHIFT) & HDR_NT_MASK);
                             const bool imag = ha & HDR_IMAG;
                             if (skipbit && ((31 - __builtin_clz(xl)) != (int)skipbit || imag)) return 13;  // the skip bit is the top X bit
+                            if (((kind & KIND_XROW) != 0) != ((xl & 15u) != 0)) return 21;  // X bits on register rows are flagged
                             cplx w(0.0, 0.0);
                             // walk the runs exactly as the kernel does: the first term of a run carries its length
                             int64_t tt = tb;

@@ -44,9 +44,8 @@ print(g)
 print("total group visits (per amplitude):", g.group_visits.sum(), " term visits:", g.term_visits.sum())
 # X bits in the register rows / lanes / row blocks
 xw = df.xword.values
-print("groups with X only in reg+lane bits (no half-visit possible):", int(((xw >> 8) == 0).sum()), " with X only in reg bits:", int(((xw >> 3) == 0).sum()))
+print("groups with no X bit on a row-block position (no half-visit possible):", int(((xw >> 9) == 0).sum()), " with X bits on register rows:", int(((xw & 15) != 0).sum()))
 per = df.groupby("sweep").agg(groups=("nt", "size"), terms=("nt", "sum"))
 print(per.describe().T)
-xl = xw ^ ((xw >> 3) & 7)  # tile_word_of is an involution
-df["xweight"] = [bin(int(v)).count("1") for v in xl]
+df["xweight"] = [bin(int(v)).count("1") for v in xw]
 print(df.groupby(["xweight", "kind"]).agg(groups=("nt", "size"), terms=("nt", "sum"), nt_mean=("nt", "mean"), nt_max=("nt", "max")))
