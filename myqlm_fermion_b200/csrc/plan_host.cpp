@@ -94,6 +94,17 @@ uint64_t tile_natural_spread(const SweepHost& s, uint32_t nat) {
 
 namespace {
 
+// bits of `mask` on the outer positions (outside the tile mask), packed in the order tile_base deposits the tile number
+uint32_t compress_outer(const SweepHost& s, uint64_t mask) {
+    uint32_t out = 0;
+    int at = 0;
+    for (int r = 0; r < s.n_runs; ++r) {
+        out |= (uint32_t)((mask >> s.run_pos[r]) & ((uint64_t(1) << s.run_len[r]) - 1)) << at;
+        at += s.run_len[r];
+    }
+    return out;
+}
+
 void append_tables(const SweepHost& s, PlanHost& out) {
     for (uint32_t e = 0; e < (uint32_t)PLAN_TABLE; ++e) {
         const uint32_t idx = e < 128 ? e : ((e - 128) << 7);  // entries 0..127: index bits 0..6; 128..191: bits 7..12
@@ -436,6 +447,7 @@ int build_plan(const TermView& t, int n_local, int shard, const PlanLimits& lim,
                         out.t_zl.push_back((zl & TZ_HI_MASK) | (v << TZ_V_SHIFT));
                         out.t_zl[run_head] += 1u << TZ_RUN_SHIFT;
                         out.t_zo.push_back((recs[i].z & lomask) & ~L);
+                        out.t_zoc.push_back(compress_outer(s, (recs[i].z & lomask) & ~L));
                         out.t_cre.push_back(gi.imag ? recs[i].im : recs[i].re);
                         out.t_cim.push_back(gi.imag ? 0.0 : recs[i].im);
                     }
@@ -444,6 +456,7 @@ int build_plan(const TermView& t, int n_local, int shard, const PlanLimits& lim,
                         out.t_zl.push_back(out.t_zl.back() & ~(0xfffu << TZ_RUN_SHIFT));
                         out.t_zl[run_head] += 1u << TZ_RUN_SHIFT;
                         out.t_zo.push_back(out.t_zo.back());
+                        out.t_zoc.push_back(out.t_zoc.back());
                         out.t_cre.push_back(0.0);
                         out.t_cim.push_back(0.0);
                         ++nt_emit;

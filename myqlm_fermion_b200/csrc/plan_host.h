@@ -112,6 +112,7 @@ struct PlanHost {
     std::vector<uint32_t> nat_loc;
     std::vector<uint32_t> t_zl;    // staged term word, see the TZ_* constants
     std::vector<uint64_t> t_zo;    // shard-local z bits outside the tile
+    std::vector<uint32_t> t_zoc;   // the same bits packed against the tile number: sign of the term on tile t = parity(t_zoc & t)
     std::vector<double> t_cre, t_cim;  // gather-form coefficients, rank sign folded; imag groups keep Im in t_cre
     // direct layout (class order, original term order inside a class)
     std::vector<uint64_t> d_x, d_z;  // shard-local masks

@@ -53,6 +53,11 @@ template <> struct __align__(16) TermRec<double, true> { double c; double ci; ui
 template <> struct __align__(8) TermRec<float, false> { float c; uint32_t zp; };
 template <> struct __align__(16) TermRec<float, true> { float c; float ci; uint32_t zp; uint32_t pad; };
 
+// one staged term of a real-coefficient sweep as it travels in the kernel parameter (constant bank): coefficient as on tile 0
+// (double, or float in c_lo for complex64 states), the word t_zl and the packed outer z bits t_zoc of plan_host.h
+struct TermConst { uint32_t c_lo, c_hi, zp, zoc; };
+constexpr int SWEEP_CONST_TERMS = 1920;  // 30 KB of the 32 KB a kernel may take as parameters
+
 struct SweepArgs {
     const void* ket;
     const void* bra;
@@ -61,7 +66,7 @@ struct SweepArgs {
     const uint32_t* g_hdr;
     const uint32_t* r_desc;
     const uint32_t* t_zl;
-    const uint64_t* t_zo;
+    const uint32_t* t_zoc;
     const double* t_cre;
     const double* t_cim;
     int n_groups, n_terms, n_ranges;
@@ -74,6 +79,7 @@ struct SweepArgs {
     unsigned long long ket_xor;
     uint8_t run_pos[PLAN_MAX_RUNS];
     uint8_t run_len[PLAN_MAX_RUNS];
+    TermConst tc[SWEEP_CONST_TERMS];  // real-coefficient sweeps only
 };
 
 // Fixed shared-memory map (bytes), sized for the largest sweep (2^13 complex128 amplitudes, 2048 complex-coefficient terms):
@@ -87,9 +93,10 @@ constexpr uint32_t SM_RNG = SM_HDR + 4096;              // 2 KB range descriptor
 constexpr uint32_t SM_NATOFF = SM_RNG + 2048;           // index tables of the sweep (plan_host.h)
 constexpr uint32_t SM_LOCOFF = SM_NATOFF + PLAN_TABLE * 8;
 constexpr uint32_t SM_NATLOC = SM_LOCOFF + PLAN_TABLE * 8;
-constexpr uint32_t SM_RED = SM_NATLOC + PLAN_TABLE * 4; // block reduction scratch
+constexpr uint32_t SM_ZOC = SM_NATLOC + PLAN_TABLE * 4; // 8 KB: z bits of the staged terms outside the tile, packed against the tile number
+constexpr uint32_t SM_RED = SM_ZOC + 2048 * 4;          // block reduction scratch
 constexpr uint32_t SM_TOTAL = SM_RED + NW * 16;
-constexpr int SWEEP_MAX_TERMS = 2048, SWEEP_MAX_GROUPS = 512;  // ranges per sweep <= 7 skip levels x 2 polarities x 2 kinds
+constexpr int SWEEP_MAX_TERMS = SWEEP_CONST_TERMS, SWEEP_MAX_GROUPS = 512;  // ranges per sweep <= 7 skip levels x 2 polarities x 2 kinds
 constexpr int BATCH_MAX_TERMS = 1024, BATCH_MAX_GROUPS = 128;
 static_assert((size_t)NW * BATCH_MAX_GROUPS * 16 <= 32768 && BATCH_MAX_TERMS * 32 <= 32768, "batch accumulators share the term area");
 static_assert(SM_TOTAL <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
@@ -172,19 +179,55 @@ __device__ __forceinline__ cplx_t partner_row(const cplx_t* __restrict__ pp, con
     return XROW ? pp[((uint32_t)r ^ xr) * PLANE] : pp[(uint32_t)r * PLANE];
 }
 
+// Where the staged terms of a sweep live.  Complex-coefficient sweeps keep them in shared memory (TermRec, signs flipped in place per
+// tile).  Real-coefficient sweeps read them from the kernel parameter: indexed constant-bank loads run beside the shared-memory
+// pipe, which the partner rows saturate (a broadcast LDS.128 costs 2 of its cycles, measured); the sign of the z bits outside the
+// tile joins the parity, parity(A) ^ parity(B) = parity(A ^ B).
+template <typename real_t, bool CPLX> struct Terms;
+template <typename real_t> struct Terms<real_t, true> {
+    const TermRec<real_t, true>* rec;
+    __device__ __forceinline__ void load(const int t, const uint32_t jhi, real_t& c, real_t& ci, uint32_t& par) const {
+        uint32_t zp;
+        load_rec(rec + t, c, ci, zp);
+        par = (uint32_t)__popc(zp & jhi);
+    }
+    __device__ __forceinline__ uint32_t head(const int t) const { return rec[t].zp; }
+};
+template <> struct Terms<double, false> {
+    const SweepArgs& a;
+    uint32_t tile;
+    __device__ __forceinline__ void load(const int t, const uint32_t jhi, double& c, double& ci, uint32_t& par) const {
+        const TermConst& q = a.tc[t];
+        c = __hiloint2double((int)q.c_hi, (int)q.c_lo);
+        ci = 0.0;
+        par = (uint32_t)__popc((q.zp & jhi) ^ (q.zoc & tile));
+    }
+    __device__ __forceinline__ uint32_t head(const int t) const { return a.tc[t].zp; }
+};
+template <> struct Terms<float, false> {
+    const SweepArgs& a;
+    uint32_t tile;
+    __device__ __forceinline__ void load(const int t, const uint32_t jhi, float& c, float& ci, uint32_t& par) const {
+        const TermConst& q = a.tc[t];
+        c = __uint_as_float(q.c_lo);
+        ci = 0.0f;
+        par = (uint32_t)__popc((q.zp & jhi) ^ (q.zoc & tile));
+    }
+    __device__ __forceinline__ uint32_t head(const int t) const { return a.tc[t].zp; }
+};
+
 // S = sum_t c_t (-1)^{|z_t & jhi|} over the staged terms [t, te).  jhi only has lane / row-block bits set, so the run fields in the
 // upper half of the term word never reach the popc.  EVEN: te - t is even (KIND_FAST lists are padded): two independent chains.
 template <typename real_t, bool CPLX, bool EVEN>
-__device__ __forceinline__ void signed_sum(const TermRec<real_t, CPLX>* __restrict__ s_rec, int t, const int te, const uint32_t jhi, real_t& Sre, real_t& Sim) {
+__device__ __forceinline__ void signed_sum(const Terms<real_t, CPLX>& terms, int t, const int te, const uint32_t jhi, real_t& Sre, real_t& Sim) {
     real_t S0 = (real_t)0, S1 = (real_t)0, I0 = (real_t)0, I1 = (real_t)0;
     if (EVEN) {
 #pragma unroll 1
         for (; t < te; t += 2) {
             real_t c0, c1, d0, d1;
-            uint32_t z0, z1;
-            load_rec(s_rec + t, c0, d0, z0);
-            load_rec(s_rec + t + 1, c1, d1, z1);
-            const uint32_t p0 = (uint32_t)__popc(z0 & jhi), p1 = (uint32_t)__popc(z1 & jhi);
+            uint32_t p0, p1;
+            terms.load(t, jhi, c0, d0, p0);
+            terms.load(t + 1, jhi, c1, d1, p1);
             S0 += sign_by_parity(c0, p0);
             S1 += sign_by_parity(c1, p1);
             if (CPLX) {
@@ -196,15 +239,46 @@ __device__ __forceinline__ void signed_sum(const TermRec<real_t, CPLX>* __restri
 #pragma unroll 1
         for (; t < te; ++t) {
             real_t c0, d0;
-            uint32_t z0;
-            load_rec(s_rec + t, c0, d0, z0);
-            const uint32_t p0 = (uint32_t)__popc(z0 & jhi);
+            uint32_t p0;
+            terms.load(t, jhi, c0, d0, p0);
             S0 += sign_by_parity(c0, p0);
             if (CPLX) I0 += sign_by_parity(d0, p0);
         }
     }
     Sre = S0 + S1;
     Sim = I0 + I1;
+}
+
+// the same sum for a compile-time term count: all loads are issued before the first use (KIND_FAST groups of 2, 4 or 6 terms)
+template <typename real_t, bool CPLX, int N>
+__device__ __forceinline__ void signed_sum_fixed(const Terms<real_t, CPLX>& terms, const int t, const uint32_t jhi, real_t& Sre, real_t& Sim) {
+    real_t c[N], d[N];
+    uint32_t p[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) terms.load(t + i, jhi, c[i], d[i], p[i]);
+    real_t S0 = (real_t)0, S1 = (real_t)0, I0 = (real_t)0, I1 = (real_t)0;
+#pragma unroll
+    for (int i = 0; i < N; i += 2) {
+        S0 += sign_by_parity(c[i], p[i]);
+        S1 += sign_by_parity(c[i + 1], p[i + 1]);
+        if (CPLX) {
+            I0 += sign_by_parity(d[i], p[i]);
+            I1 += sign_by_parity(d[i + 1], p[i + 1]);
+        }
+    }
+    Sre = S0 + S1;
+    Sim = I0 + I1;
+}
+
+// KIND_FAST term sum: the common even counts are straight-line code
+template <typename real_t, bool CPLX>
+__device__ __forceinline__ void signed_sum_fast(const Terms<real_t, CPLX>& terms, const int t, const int nt, const uint32_t jhi, real_t& Sre, real_t& Sim) {
+    switch (nt) {
+        case 2: signed_sum_fixed<real_t, CPLX, 2>(terms, t, jhi, Sre, Sim); break;
+        case 4: signed_sum_fixed<real_t, CPLX, 4>(terms, t, jhi, Sre, Sim); break;
+        case 6: signed_sum_fixed<real_t, CPLX, 6>(terms, t, jhi, Sre, Sim); break;
+        default: signed_sum<real_t, CPLX, true>(terms, t, t + nt, jhi, Sre, Sim); break;
+    }
 }
 
 // sum_r (-1)^{v.r} f_r over N = 2^m rows with the low m bits of v: m halving steps of fused multiply-adds
@@ -245,14 +319,14 @@ __device__ __forceinline__ void times_weight(real_t& sr, real_t& si, const real_
 
 // <own| G |tile> of one group for the thread's 16 rows: sum_r conj(own_r) Wc(r) p_r with p_r the partner of row r.
 template <typename real_t, bool CPLX, int KIND>
-__device__ __forceinline__ void group_value_full(const typename CplxOf<real_t>::type* __restrict__ pp, const uint32_t xr, const TermRec<real_t, CPLX>* __restrict__ s_rec,
+__device__ __forceinline__ void group_value_full(const typename CplxOf<real_t>::type* __restrict__ pp, const uint32_t xr, const Terms<real_t, CPLX>& terms,
                                                  const int tb, const int nt, const bool imag, const uint32_t jhi,
                                                  const typename CplxOf<real_t>::type (&own)[R], real_t& out_re, real_t& out_im) {
     using cplx_t = typename CplxOf<real_t>::type;
     (void)xr;
     if (KIND == KIND_FAST) {
         real_t Sre, Sim;
-        signed_sum<real_t, CPLX, true>(s_rec, tb, tb + nt, jhi, Sre, Sim);
+        signed_sum_fast<real_t, CPLX>(terms, tb, nt, jhi, Sre, Sim);
         real_t a0 = (real_t)0, a1 = (real_t)0, b0 = (real_t)0, b1 = (real_t)0;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -283,11 +357,11 @@ __device__ __forceinline__ void group_value_full(const typename CplxOf<real_t>::
             const int te = tb + nt;
 #pragma unroll 1
             while (t < te) {
-                const uint32_t head = s_rec[t].zp;
+                const uint32_t head = terms.head(t);
                 const uint32_t v = (head >> TZ_V_SHIFT) & 15u;
                 const int len = (int)(head >> TZ_RUN_SHIFT);
                 real_t Sre, Sim;
-                signed_sum<real_t, CPLX, false>(s_rec, t, t + len, jhi, Sre, Sim);
+                signed_sum<real_t, CPLX, false>(terms, t, t + len, jhi, Sre, Sim);
                 t += len;
                 real_t sr = fold_rows<real_t, 8>(fr, v), si = fold_rows<real_t, 8>(fi, v);
                 if (ch) {
@@ -307,15 +381,17 @@ __device__ __forceinline__ void group_value_full(const typename CplxOf<real_t>::
 
 // All groups of one range (same skip bit, polarity and kind) for the thread's 16 rows.
 template <typename real_t, bool CPLX, int MODE, int KIND>
-__device__ __forceinline__ void process_range(const typename CplxOf<real_t>::type* __restrict__ tile, const TermRec<real_t, CPLX>* __restrict__ s_rec,
+__device__ __forceinline__ void process_range(const typename CplxOf<real_t>::type* __restrict__ tile, const Terms<real_t, CPLX>& terms,
                                               const uint2* __restrict__ s_hdr, double2* __restrict__ s_acc_warp, const int g0, const int g1, int tb,
                                               const uint32_t w0, const uint32_t jhi, const bool half,
                                               const typename CplxOf<real_t>::type (&own)[R], real_t (&acc_re)[R], real_t (&acc_im)[R],
                                               double& e_re, double& e_im) {
     using cplx_t = typename CplxOf<real_t>::type;
+    uint32_t hdr_next = s_hdr[g0].x;
 #pragma unroll 1
     for (int g = g0; g < g1; ++g) {
-        const uint32_t hdr = s_hdr[g].x;
+        const uint32_t hdr = hdr_next;
+        if (g + 1 < g1) hdr_next = s_hdr[g + 1].x;  // next group's header travels while this group is processed
         const cplx_t* __restrict__ pp = tile + (w0 ^ ((hdr & HDR_XL_MASK) >> RB));  // partner thread's word of plane 0
         const uint32_t xr = hdr & (uint32_t)(R - 1);
         const int nt = (int)((hdr >> HDR_NT_SHIFT) & HDR_NT_MASK);
@@ -325,7 +401,7 @@ __device__ __forceinline__ void process_range(const typename CplxOf<real_t>::typ
             // skip bit equals the range polarity get here.
             if (KIND == KIND_FAST) {
                 real_t S, Si;
-                signed_sum<real_t, false, true>(reinterpret_cast<const TermRec<real_t, false>*>(s_rec), tb, tb + nt, jhi, S, Si);
+                signed_sum_fast<real_t, CPLX>(terms, tb, nt, jhi, S, Si);
                 real_t a0 = (real_t)0, a1 = (real_t)0, a2 = (real_t)0, a3 = (real_t)0;  // independent chains keep the FP64 pipe busy
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
@@ -351,11 +427,11 @@ __device__ __forceinline__ void process_range(const typename CplxOf<real_t>::typ
                 real_t tot = (real_t)0;
 #pragma unroll 1
                 while (t < te) {
-                    const uint32_t head = s_rec[t].zp;
+                    const uint32_t head = terms.head(t);
                     const uint32_t v = (head >> TZ_V_SHIFT) & 15u;
                     const int len = (int)(head >> TZ_RUN_SHIFT);
                     real_t S, Si;
-                    signed_sum<real_t, false, false>(reinterpret_cast<const TermRec<real_t, false>*>(s_rec), t, t + len, jhi, S, Si);
+                    signed_sum<real_t, CPLX, false>(terms, t, t + len, jhi, S, Si);
                     t += len;
                     tot = fma(S, fold_rows<real_t, R>(f, v), tot);
                 }
@@ -363,7 +439,7 @@ __device__ __forceinline__ void process_range(const typename CplxOf<real_t>::typ
             }
         } else if (MODE == MODE_EXPECT || MODE == MODE_BATCH) {
             real_t sr, si;
-            group_value_full<real_t, CPLX, KIND>(pp, xr, s_rec, tb, nt, imag, jhi, own, sr, si);
+            group_value_full<real_t, CPLX, KIND>(pp, xr, terms, tb, nt, imag, jhi, own, sr, si);
             if (MODE == MODE_EXPECT) {
                 e_re += (double)sr;
                 e_im += (double)si;
@@ -384,7 +460,7 @@ __device__ __forceinline__ void process_range(const typename CplxOf<real_t>::typ
         } else {  // MODE_APPLY: acc_r += Wc(r) p_r
             if (KIND == KIND_FAST) {
                 real_t Sre, Sim;
-                signed_sum<real_t, CPLX, true>(s_rec, tb, tb + nt, jhi, Sre, Sim);
+                signed_sum_fast<real_t, CPLX>(terms, tb, nt, jhi, Sre, Sim);
                 // Wc = wr + i wi
                 const real_t wr = (!CPLX && imag) ? (real_t)0 : Sre;
                 const real_t wi = CPLX ? Sim : (imag ? Sre : (real_t)0);
@@ -412,11 +488,11 @@ __device__ __forceinline__ void process_range(const typename CplxOf<real_t>::typ
                     const int te = tb + nt;
 #pragma unroll 1
                     while (t < te) {
-                        const uint32_t head = s_rec[t].zp;
+                        const uint32_t head = terms.head(t);
                         const uint32_t v = (head >> TZ_V_SHIFT) & 15u;
                         const int len = (int)(head >> TZ_RUN_SHIFT);
                         real_t Sre, Sim;
-                        signed_sum<real_t, CPLX, false>(s_rec, t, t + len, jhi, Sre, Sim);
+                        signed_sum<real_t, CPLX, false>(terms, t, t + len, jhi, Sre, Sim);
                         t += len;
                         if (ch) {
                             const real_t s3 = sigma<real_t>(v, 3);
@@ -467,6 +543,27 @@ __device__ __forceinline__ void process_range(const typename CplxOf<real_t>::typ
     }
 }
 
+// sign of staged term t on tile T = parity(zoc_t & T) (z bits outside the tile against the tile number): moving from tile T' to T
+// flips the terms with odd |zoc_t & (T ^ T')|, in place
+template <typename real_t, bool CPLX>
+__device__ __forceinline__ void flip_signs(TermRec<real_t, CPLX>* __restrict__ s_rec, const uint32_t* __restrict__ s_zoc, const int nT, const uint32_t diff) {
+    if (diff == 0) return;
+    for (int t = threadIdx.x; t < nT; t += NT) {
+        if (__popc(s_zoc[t] & diff) & 1) {
+            s_rec[t].c = -s_rec[t].c;
+            if constexpr (CPLX) s_rec[t].ci = -s_rec[t].ci;
+        }
+    }
+}
+
+template <typename real_t, bool CPLX>
+__device__ __forceinline__ Terms<real_t, CPLX> make_terms(const SweepArgs& a, const TermRec<real_t, CPLX>* s_rec, const uint32_t tile) {
+    if constexpr (CPLX)
+        return Terms<real_t, true>{s_rec};
+    else
+        return Terms<real_t, false>{a, tile};
+}
+
 template <typename real_t, bool CPLX, int MODE>
 __global__ void __launch_bounds__(NT, 1) tile_sweep_kernel(const __grid_constant__ SweepArgs a) {
     using cplx_t = typename CplxOf<real_t>::type;
@@ -482,6 +579,7 @@ __global__ void __launch_bounds__(NT, 1) tile_sweep_kernel(const __grid_constant
     uint64_t* s_nat_off = reinterpret_cast<uint64_t*>(smem + SM_NATOFF);
     uint64_t* s_loc_off = reinterpret_cast<uint64_t*>(smem + SM_LOCOFF);
     uint32_t* s_nat_loc = reinterpret_cast<uint32_t*>(smem + SM_NATLOC);
+    uint32_t* s_zoc = reinterpret_cast<uint32_t*>(smem + SM_ZOC);
     double2* s_acc = reinterpret_cast<double2*>(smem + SM_ACC);
     double2* s_red = reinterpret_cast<double2*>(smem + SM_RED);
 
@@ -498,7 +596,16 @@ __global__ void __launch_bounds__(NT, 1) tile_sweep_kernel(const __grid_constant
         s_loc_off[i] = a.loc_off[i];
         s_nat_loc[i] = a.nat_loc[i];
     }
-    for (int t = tid; t < nT; t += NT) s_rec[t].zp = a.t_zl[t];
+    // staged terms: coefficients as on tile 0; every tile flips the signs that change against the previous tile it staged
+    if constexpr (CPLX) {
+        for (int t = tid; t < nT; t += NT) {
+            s_rec[t].zp = a.t_zl[t];
+            s_rec[t].c = (real_t)a.t_cre[t];
+            s_rec[t].ci = (real_t)a.t_cim[t];
+            s_zoc[t] = a.t_zoc[t];
+        }
+    }
+    unsigned long long prev_tile = 0;
     if (MODE == MODE_BATCH)
         for (int i = tid; i < NW * nG; i += NT) s_acc[i] = make_double2(0.0, 0.0);
 
@@ -523,38 +630,42 @@ __global__ void __launch_bounds__(NT, 1) tile_sweep_kernel(const __grid_constant
         {
             const uint64_t kbase = base ^ a.ket_xor;
             // the tile is enumerated in natural order (consecutive threads = consecutive amplitudes of a 128 B segment) and
-            // scattered to its tile-local words; full tiles keep 8 independent 128-bit loads in flight per step
-            if (tile_amps >= 8 * NT) {
-                for (uint32_t i0 = tid; i0 < tile_amps; i0 += 8 * NT) {
-                    cplx_t v[8];
+            // scattered to its tile-local words; a full tile is one batch of 16 independent 128-bit loads per thread
+            if (tile_amps == R * NT) {
+                cplx_t v[R];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const uint32_t idx = i0 + u * NT;
-                        v[u] = ld_stream(ket + (kbase | s_nat_off[idx & 127] | s_nat_off[128 + (idx >> 7)]));
-                    }
+                for (int u = 0; u < R; ++u) {
+                    const uint32_t idx = tid + u * NT;
+                    v[u] = ld_stream(ket + (kbase | s_nat_off[idx & 127] | s_nat_off[128 + (idx >> 7)]));
+                }
+                if constexpr (CPLX) flip_signs<real_t, CPLX>(s_rec, s_zoc, nT, (uint32_t)(tile_id ^ prev_tile));  // shared memory only: overlaps the loads
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const uint32_t idx = i0 + u * NT;
-                        tile[tile_word(s_nat_loc[idx & 127] | s_nat_loc[128 + (idx >> 7)])] = v[u];
-                    }
+                for (int u = 0; u < R; ++u) {
+                    const uint32_t idx = tid + u * NT;
+                    tile[tile_word(s_nat_loc[idx & 127] | s_nat_loc[128 + (idx >> 7)])] = v[u];
                 }
             } else {
+                if constexpr (CPLX) flip_signs<real_t, CPLX>(s_rec, s_zoc, nT, (uint32_t)(tile_id ^ prev_tile));
                 for (uint32_t idx = tid; idx < tile_amps; idx += NT)
                     tile[tile_word(s_nat_loc[idx & 127] | s_nat_loc[128 + (idx >> 7)])] =
                         ld_stream(ket + (kbase | s_nat_off[idx & 127] | s_nat_off[128 + (idx >> 7)]));
             }
-            // coefficients with the sign of the z bits outside the tile (constant over the tile)
-            for (int t = tid; t < nT; t += NT) {
-                const bool neg = __popcll(a.t_zo[t] & base) & 1;
-                const double cr = a.t_cre[t];
-                s_rec[t].c = (real_t)(neg ? -cr : cr);
-                if constexpr (CPLX) {
-                    const double ci = a.t_cim[t];
-                    s_rec[t].ci = (real_t)(neg ? -ci : ci);
-                }
-            }
+            prev_tile = tile_id;
         }
         __syncthreads();
+        // next tile of this CTA -> L2 while this one is processed (two 128 B lines per thread)
+        if (tile_id + gridDim.x < a.n_tiles) {
+            uint64_t nbase = 0;
+            unsigned long long rest = tile_id + gridDim.x;
+            for (int r = 0; r < a.n_runs; ++r) {
+                const int len = a.run_len[r];
+                nbase |= (rest & ((1ull << len) - 1ull)) << a.run_pos[r];
+                rest >>= len;
+            }
+            nbase ^= a.ket_xor;
+            for (uint32_t idx = 8u * tid; idx < tile_amps; idx += 8u * NT)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(ket + (nbase | s_nat_off[idx & 127] | s_nat_off[128 + (idx >> 7)])));
+        }
 
         if (active) {
             real_t acc_re[R], acc_im[R];
@@ -574,6 +685,7 @@ __global__ void __launch_bounds__(NT, 1) tile_sweep_kernel(const __grid_constant
                 }
             }
             double2* s_acc_warp = s_acc + (size_t)warp * nG;
+            const Terms<real_t, CPLX> terms = make_terms<real_t, CPLX>(a, s_rec, (uint32_t)tile_id);
 #pragma unroll 1
             for (int ri = 0; ri < nR; ++ri) {
                 const uint2 d = s_rng[ri];
@@ -587,11 +699,11 @@ __global__ void __launch_bounds__(NT, 1) tile_sweep_kernel(const __grid_constant
                 const int g0 = (int)(d.x & 0xffffu), g1 = (int)(d.x >> 16), t0 = (int)(d.y & 0xffffu);
                 const uint32_t kind = (d.y >> RNG_KIND_SHIFT) & 3u;
                 if (kind == KIND_FAST)
-                    process_range<real_t, CPLX, MODE, KIND_FAST>(tile, s_rec, s_hdr, s_acc_warp, g0, g1, t0, w0, jhi, half, own, acc_re, acc_im, e_re, e_im);
+                    process_range<real_t, CPLX, MODE, KIND_FAST>(tile, terms, s_hdr, s_acc_warp, g0, g1, t0, w0, jhi, half, own, acc_re, acc_im, e_re, e_im);
                 else if (kind == KIND_RUNS)
-                    process_range<real_t, CPLX, MODE, KIND_RUNS>(tile, s_rec, s_hdr, s_acc_warp, g0, g1, t0, w0, jhi, half, own, acc_re, acc_im, e_re, e_im);
+                    process_range<real_t, CPLX, MODE, KIND_RUNS>(tile, terms, s_hdr, s_acc_warp, g0, g1, t0, w0, jhi, half, own, acc_re, acc_im, e_re, e_im);
                 else
-                    process_range<real_t, CPLX, MODE, KIND_RUNS | KIND_XROW>(tile, s_rec, s_hdr, s_acc_warp, g0, g1, t0, w0, jhi, half, own, acc_re, acc_im, e_re, e_im);
+                    process_range<real_t, CPLX, MODE, KIND_RUNS | KIND_XROW>(tile, terms, s_hdr, s_acc_warp, g0, g1, t0, w0, jhi, half, own, acc_re, acc_im, e_re, e_im);
             }
             if (MODE == MODE_APPLY) {
 #pragma unroll
@@ -733,7 +845,7 @@ struct qfe_plan {
     bool batch = false;
     bool force_direct = false;
     int device = 0;
-    DevBuf g_hdr, r_desc, t_zl, t_zo, t_cre, t_cim, d_x, d_z, d_cre, d_cim, dg_begin, nat_off, loc_off, nat_loc;
+    DevBuf g_hdr, r_desc, t_zl, t_zoc, t_cre, t_cim, d_x, d_z, d_cre, d_cim, dg_begin, nat_off, loc_off, nat_loc;
 };
 
 namespace qfe {
@@ -784,12 +896,12 @@ static int launch_direct(qfe_ctx* ctx, const DirectArgs& args, dim3 grid, int dt
     return QFE_OK;
 }
 
-static void fill_sweep_args(const qfe_plan* p, const SweepHost& s, SweepArgs& a) {
+static void fill_sweep_args(const qfe_plan* p, const SweepHost& s, int dtype, SweepArgs& a) {
     a.g_hdr = p->g_hdr.as<uint32_t>() + 2 * (size_t)s.group_begin;
     a.r_desc = p->r_desc.as<uint32_t>() + 2 * (size_t)s.range_begin;
     a.n_ranges = s.range_end - s.range_begin;
     a.t_zl = p->t_zl.as<uint32_t>() + s.term_begin;
-    a.t_zo = p->t_zo.as<uint64_t>() + s.term_begin;
+    a.t_zoc = p->t_zoc.as<uint32_t>() + s.term_begin;
     a.t_cre = p->t_cre.as<double>() + s.term_begin;
     a.t_cim = p->t_cim.as<double>() + s.term_begin;
     a.n_groups = s.group_end - s.group_begin;
@@ -801,6 +913,25 @@ static void fill_sweep_args(const qfe_plan* p, const SweepHost& s, SweepArgs& a)
     memcpy(a.run_pos, s.run_pos, sizeof(a.run_pos));
     memcpy(a.run_len, s.run_len, sizeof(a.run_len));
     const size_t si = (size_t)(&s - p->h.sweeps.data());
+    if (!s.complex_w) {  // real-coefficient sweep: the staged terms travel in the kernel parameter
+        const PlanHost& h = p->h;
+        for (int t = 0; t < a.n_terms; ++t) {
+            const int64_t i = s.term_begin + t;
+            TermConst& q = a.tc[t];
+            if (dtype == QFE_C128) {
+                uint64_t bits;
+                memcpy(&bits, &h.t_cre[i], 8);
+                q.c_lo = (uint32_t)bits;
+                q.c_hi = (uint32_t)(bits >> 32);
+            } else {
+                const float f = (float)h.t_cre[i];
+                memcpy(&q.c_lo, &f, 4);
+                q.c_hi = 0;
+            }
+            q.zp = h.t_zl[i];
+            q.zoc = h.t_zoc[i];
+        }
+    }
     a.nat_off = p->nat_off.as<uint64_t>() + si * PLAN_TABLE;
     a.loc_off = p->loc_off.as<uint64_t>() + si * PLAN_TABLE;
     a.nat_loc = p->nat_loc.as<uint32_t>() + si * PLAN_TABLE;
@@ -838,7 +969,7 @@ static int run_class_reduce(qfe_ctx* ctx, const qfe_plan* p, int ci, const void*
             const SweepHost& sw = p->h.sweeps[si];
             SweepArgs a;
             memset(&a, 0, sizeof(a));
-            fill_sweep_args(p, sw, a);
+            fill_sweep_args(p, sw, dtype, a);
             a.ket = ket;
             a.bra = bra;
             a.same_tile = (bra == ket && sw.ket_xor == 0) ? 1 : 0;
@@ -941,7 +1072,7 @@ int qfe_plan_create(qfe_ctx* ctx, const qfe_terms* t, int n_local, int shard, in
     }
     cudaStream_t s = ctx->stream;
     int rc = QFE_OK;
-    if ((rc = upload(p->g_hdr, p->h.g_hdr, s)) || (rc = upload(p->r_desc, p->h.r_desc, s)) || (rc = upload(p->t_zl, p->h.t_zl, s)) || (rc = upload(p->t_zo, p->h.t_zo, s)) ||
+    if ((rc = upload(p->g_hdr, p->h.g_hdr, s)) || (rc = upload(p->r_desc, p->h.r_desc, s)) || (rc = upload(p->t_zl, p->h.t_zl, s)) || (rc = upload(p->t_zoc, p->h.t_zoc, s)) ||
         (rc = upload(p->t_cre, p->h.t_cre, s)) || (rc = upload(p->t_cim, p->h.t_cim, s)) || (rc = upload(p->d_x, p->h.d_x, s)) ||
         (rc = upload(p->d_z, p->h.d_z, s)) || (rc = upload(p->d_cre, p->h.d_cre, s)) || (rc = upload(p->d_cim, p->h.d_cim, s)) ||
         (rc = upload(p->dg_begin, p->h.dg_begin, s)) || (rc = upload(p->nat_off, p->h.nat_off, s)) || (rc = upload(p->loc_off, p->h.loc_off, s)) ||
@@ -1044,7 +1175,7 @@ int qfe_apply_class(qfe_ctx* ctx, const qfe_plan* p, int x_hi, const void* ket, 
             const SweepHost& sw = p->h.sweeps[si];
             SweepArgs a;
             memset(&a, 0, sizeof(a));
-            fill_sweep_args(p, sw, a);
+            fill_sweep_args(p, sw, dtype, a);
             a.ket = ket;
             a.bra = ket;
             a.out_vec = y;

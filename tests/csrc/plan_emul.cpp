@@ -77,6 +77,8 @@ extern "C" int plan_emul_run(int n, int64_t T, const uint64_t* x, const uint64_t
             for (int64_t t = 0; t < s.n_tiles; ++t) {
                 const uint64_t base = tile_base(s, (uint64_t)t);
                 if (base & s.tile_mask) return 4;
+                for (int64_t tt = s.term_begin; tt < s.term_end; ++tt)  // packed outer z bits against the tile number
+                    if ((__builtin_popcountll(p.t_zo[tt] & base) ^ __builtin_popcount(p.t_zoc[tt] & (uint32_t)t)) & 1) return 27;
                 for (uint32_t j = 0; j < tile_amps; ++j) {
                     const uint64_t pos = tile_spread(s, j);
                     if (pos & ~s.tile_mask) return 5;

@@ -88,6 +88,36 @@ __global__ void __launch_bounds__(NT, 1) k(const __grid_constant__ Params prm, d
                     }
                 }
             }
+        } else if (MODE == 8) {  // partner-row LDS.128 x16 interleaved with 8 indexed LDC.64 (constant path next to the shared path)
+            uint32_t w = (tid << 4) ^ ((tid) & 7);
+            for (int it = 0; it < ITER; ++it) {
+                const uint32_t pw = w ^ ((it * 37) & 0x1ff0);
+                const uint32_t b = ((it * 37 + stride_sel * lane) & 0x7f0);
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    const double2 p = tile[pw ^ r];
+                    acc0 += p.x;
+                    acc1 += p.y;
+                    if (r & 1) acc1 += prm.c[b + (r >> 1)];
+                }
+            }
+        } else if (MODE == 9) {  // partner-row LDS.128 x16 interleaved with 4 broadcast LDS.128 (today's term records)
+            uint32_t w = (tid << 4) ^ ((tid) & 7);
+            for (int it = 0; it < ITER; ++it) {
+                const uint32_t pw = w ^ ((it * 37) & 0x1ff0);
+                const uint32_t b = ((it * 37 + stride_sel * lane) & 0x1ff0);
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    const double2 p = tile[pw ^ r];
+                    acc0 += p.x;
+                    acc1 += p.y;
+                    if ((r & 3) == 3) {
+                        const double2 q = tile[b + (r >> 2)];
+                        acc0 += q.x;
+                        acc1 += q.y;
+                    }
+                }
+            }
         } else if (MODE == 7) {  // conflict-free LDS.64 (two per amplitude)
             const double* t64 = reinterpret_cast<const double*>(smem);
             for (int it = 0; it < ITER; ++it) {
@@ -132,7 +162,7 @@ void run(const char* name, double bytes_per_load, int stride_sel, int nwarps) {
 }
 
 int main() {
-    for (int nw : {16, 8, 4}) {
+    for (int nw : {16, 8}) {
         run<0>("LDS.128 conflict-free (partner rows)", 512, 0, nw);
         run<1>("LDS.128 broadcast (term record)", 16, 0, nw);
         run<2>("LDS.64 broadcast", 8, 0, nw);
@@ -140,7 +170,8 @@ int main() {
         run<4>("LDC.64 param bank, uniform dynamic index", 8, 0, nw);
         run<5>("LDS.128 half the quarter-warps idle (lane bit 3)", 256, 0, nw);
         run<6>("LDS.128 odd lanes idle (lane bit 0)", 256, 0, nw);
-        run<7>("LDS.64 conflict-free", 256, 0, nw);
+        run<8>("16 LDS.128 partner + 8 LDC.64 indexed per iteration", 512, 0, nw);
+        run<9>("16 LDS.128 partner + 4 LDS.128 broadcast per iteration", 512, 0, nw);
     }
     return 0;
 }
