@@ -274,6 +274,19 @@ def main():
         "equiv_gbs_one_sweep_per_xmask is the HBM rate a one-pass-per-X-mask schedule would need for the same throughput",
         "equiv_gbs_one_sweep_per_xmask": plan.n_groups * shard_bytes * args.steps / sec / 1e9,
     }
+    # the resource that actually binds the sweep kernel: shared-memory bandwidth.  Algorithmic shared-memory bytes per step =
+    # one 16 B partner read per visited (X mask, amplitude) -- Hermitian X masks visit half the amplitudes -- plus one write and
+    # one read of every staged amplitude per sweep.  Peak = 128 B/clk/SM (measured: tools/ubench/smem_paths.cu) x SMs x SM clock.
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+    smem_bytes = shard_bytes * (0.5 * plan.half_groups + plan.full_groups + 2.0 * sweeps_per_step)
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    smem_peak = 128.0 * sm_count * sm_mhz * 1e6 / 1e9
+    smem_achieved = smem_bytes * args.steps / sec / 1e9
+    roofline["smem"] = {
+        "achieved": smem_achieved, "peak": smem_peak, "unit": "GB/s", "frac": smem_achieved / smem_peak,
+        "half_visit_x_masks": plan.half_groups, "full_visit_x_masks": plan.full_groups,
+        "note": "algorithmic shared-memory bytes (partner rows + tile staging) / time; peak = 128 B/clk/SM x SMs x sampled SM clock",
+    }
 
     # ---- e2e: the same step through the C-ABI call with HOST buffers (pinned), H2D inside the timed region ----
     e2e = None

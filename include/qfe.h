@@ -106,6 +106,12 @@ int qfe_terms_destroy(qfe_terms* t);
 int qfe_plan_create(qfe_ctx* ctx, const qfe_terms* t, int n_local, int shard, int tile_bits, qfe_plan** out);
 int qfe_plan_info(const qfe_plan* p, int64_t* n_sweeps, int64_t* n_groups, int64_t* n_terms, int32_t* n_classes, int32_t* tile_bits);
 int qfe_plan_geometry(const qfe_plan* p, int* nqbits, int* n_local);
+/* work of one <psi|H|psi> on this plan, for the roofline model of bench.py: groups (X masks) of the tiled layout that are visited on
+ * half the rows of a tile (Hermitian pairs) and on all rows, and the staged terms of both kinds, summed over the classes      */
+/* 1 when every term coefficient and constant of the planned set is real, i.e. every x_hi class is a Hermitian operator: <psi|H|psi>
+ * then needs each pair of shards (r, r^x_hi) on one of the two ranks only                                                    */
+int qfe_plan_hermitian(const qfe_plan* p, int* hermitian);
+int qfe_plan_work(const qfe_plan* p, int64_t* half_groups, int64_t* full_groups, int64_t* half_terms, int64_t* full_terms);
 /* the distinct x_hi classes, ascending (class 0 first when present)                            */
 int qfe_plan_classes(const qfe_plan* p, int32_t* x_hi, int32_t capacity);
 int qfe_plan_destroy(qfe_plan* p);
@@ -143,6 +149,18 @@ int qfe_vec_axpy(qfe_ctx* ctx, const double alpha[2], const void* x, void* y, in
 int qfe_vec_scale(qfe_ctx* ctx, const double alpha[2], void* x, int64_t n_amps, int dtype);
 int qfe_vec_fill_random(qfe_ctx* ctx, void* x, int64_t n_amps, int dtype, uint64_t seed, uint64_t offset); /* counter-based N(0,1)+iN(0,1) */
 int qfe_vec_product_state(qfe_ctx* ctx, void* x, int n_local, int shard, int nqbits, const double* alpha_beta /* 4*n doubles */, int dtype);
+/* computational-basis state on a buffer of n_amps amplitudes: all zero, amplitude `index` one (index = -1: all zero; a shard that does
+ * not hold the occupied amplitude).  Replaces the X-gate layer the reference prepends to its ansatz circuits
+ * (Hartree-Fock state, qat/fermion/chemistry/ucc.py:291-343)                                                                    */
+int qfe_vec_basis_state(qfe_ctx* ctx, void* x, int64_t n_amps, int dtype, int64_t index);
+
+/* ---- state evolution ----------------------------------------------------------------------------------------------
+ * In place psi <- exp(-i theta[K-1] P[K-1]) ... exp(-i theta[0] P[0]) psi on an unsharded state of nqbits qubits, with
+ * P[k] = i^{|x&z|} X^x Z^z (the packed-term convention, coefficient 1).  One call = the reference's
+ * make_spin_hamiltonian_trotter_slice(H, coeff) (qat/fermion/trotterisation.py:85-150) with theta[k] = coeff * Re(c_k) in the term
+ * order of H, or one layer exp(-i theta_k O_k) of the ADAPT / UCC ansatz (term by term, _grow_ansatz) (qat/plugins/adapt_vqe.py:64-141).  Consecutive rotations
+ * whose X masks fit 10 common qubits besides the 3 lowest are fused into one pass over the state.                              */
+int qfe_pauli_rotations(qfe_ctx* ctx, int nqbits, int64_t K, const uint64_t* x, const uint64_t* z, const double* theta, void* psi, int dtype);
 
 #ifdef __cplusplus
 }

@@ -44,6 +44,8 @@ SIGNATURES = {
     "qfe_terms_destroy": (C.c_int, [C.c_void_p]),
     "qfe_plan_create": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, c_void_pp]),
     "qfe_plan_info": (C.c_int, [C.c_void_p, c_i64_p, c_i64_p, c_i64_p, c_i32_p, c_i32_p]),
+    "qfe_plan_hermitian": (C.c_int, [C.c_void_p, c_int_p]),
+    "qfe_plan_work": (C.c_int, [C.c_void_p, c_i64_p, c_i64_p, c_i64_p, c_i64_p]),
     "qfe_plan_geometry": (C.c_int, [C.c_void_p, c_int_p, c_int_p]),
     "qfe_plan_classes": (C.c_int, [C.c_void_p, c_i32_p, C.c_int32]),
     "qfe_plan_destroy": (C.c_int, [C.c_void_p]),
@@ -59,6 +61,8 @@ SIGNATURES = {
     "qfe_vec_scale": (C.c_int, [C.c_void_p, c_double_p, C.c_void_p, C.c_int64, C.c_int]),
     "qfe_vec_fill_random": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_uint64, C.c_uint64]),
     "qfe_vec_product_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, c_double_p, C.c_int]),
+    "qfe_vec_basis_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int64]),
+    "qfe_pauli_rotations": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, c_u64_p, c_u64_p, c_double_p, C.c_void_p, C.c_int]),
 }
 
 

@@ -24,8 +24,9 @@
 
 namespace qfe {
 
-constexpr int NT = 512;           // threads per CTA of the tile kernel: one warp per row block of 512 amplitudes
-constexpr int NW = NT / 32;
+// Threads per CTA of the tile kernel: one warp per row block of 512 amplitudes.  Tiles of 2^13 amplitudes run as one CTA of 512
+// threads per SM; tiles of <= 2^12 as two CTAs of 256 threads per SM, so that one CTA stages its next tile while the other computes.
+constexpr int NT_MAX = 512;
 constexpr int RB = PLAN_REG_BITS; // register-blocked rows per thread: R = 16 (tile-local bits 0..3)
 constexpr int R = 1 << RB;
 // shared-memory word of tile-local index j is (j & 15) * 513 + (j >> 4): one plane of 512 words per register row, padded to an
@@ -34,7 +35,7 @@ constexpr int R = 1 << RB;
 // consecutive amplitudes a quarter warp stages land on 8 different bank groups (different planes, or consecutive words).
 static_assert(PLAN_MIN_TILE_BITS == 5 + RB, "a tile must hold at least one full warp row block");
 static_assert(PLAN_U_SHIFT == 5 + RB, "warp-uniform tile bits start above the lane and register bits");
-static_assert((1 << (PLAN_MAX_TILE_BITS - 5 - RB)) == NW, "one warp per row block of the largest tile");
+static_assert((1 << (PLAN_MAX_TILE_BITS - 5 - RB)) == NT_MAX / 32, "one warp per row block of the largest tile");
 
 // EXPECT: <bra|H|ket>; with bra tile == ket tile the own rows come from the tile and Hermitian ranges visit half the rows
 // APPLY:  y (+)= H|ket>
@@ -84,22 +85,35 @@ struct SweepArgs {
 
 // Fixed shared-memory map (bytes), sized for the largest sweep (2^13 complex128 amplitudes, 2048 complex-coefficient terms):
 // constant offsets let every access be [register + immediate] with nothing to recompute inside the group loop.
-constexpr uint32_t PLANE = PLAN_PLANE;                  // words per register-row plane
-constexpr uint32_t SM_TILE = 0;                         // 16 planes x 513 x 16 B
-constexpr uint32_t SM_REC = R * PLANE * 16;             // 64 KB staged terms (2048 x 32 B)
-constexpr uint32_t SM_ACC = SM_REC + 32768;             // BATCH only (<= 1024 terms staged): per-warp per-group accumulators, 32 KB
-constexpr uint32_t SM_HDR = SM_REC + 65536;             // 4 KB group headers (512 x 8 B)
-constexpr uint32_t SM_RNG = SM_HDR + 4096;              // 2 KB range descriptors (256 x 8 B)
-constexpr uint32_t SM_NATOFF = SM_RNG + 2048;           // index tables of the sweep (plan_host.h)
-constexpr uint32_t SM_LOCOFF = SM_NATOFF + PLAN_TABLE * 8;
-constexpr uint32_t SM_NATLOC = SM_LOCOFF + PLAN_TABLE * 8;
-constexpr uint32_t SM_ZOC = SM_NATLOC + PLAN_TABLE * 4; // 8 KB: z bits of the staged terms outside the tile, packed against the tile number
-constexpr uint32_t SM_RED = SM_ZOC + 2048 * 4;          // block reduction scratch
-constexpr uint32_t SM_TOTAL = SM_RED + NW * 16;
-constexpr int SWEEP_MAX_TERMS = SWEEP_CONST_TERMS, SWEEP_MAX_GROUPS = 512;  // ranges per sweep <= 7 skip levels x 2 polarities x 2 kinds
-constexpr int BATCH_MAX_TERMS = 1024, BATCH_MAX_GROUPS = 128;
-static_assert((size_t)NW * BATCH_MAX_GROUPS * 16 <= 32768 && BATCH_MAX_TERMS * 32 <= 32768, "batch accumulators share the term area");
-static_assert(SM_TOTAL <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
+template <int NTH> struct Geo {
+    static constexpr int NW = NTH / 32;
+    static constexpr uint32_t PLANE = NTH + 1;              // words per register-row plane (odd: see above)
+    static constexpr int CPLX_TERMS = NTH == NT_MAX ? 2048 : 1024;  // complex-coefficient terms a sweep may stage in shared memory
+    static constexpr uint32_t REC_BYTES = CPLX_TERMS * 32;
+    static constexpr uint32_t SM_TILE = 0;                  // 16 planes x (NTH + 1) x 16 B
+    static constexpr uint32_t SM_REC = R * PLANE * 16;      // staged complex-coefficient terms
+    static constexpr uint32_t SM_ACC = SM_REC + REC_BYTES / 2;  // BATCH only (half the terms staged): per-warp per-group accumulators
+    static constexpr uint32_t SM_HDR = SM_REC + REC_BYTES;  // 4 KB group headers (512 x 8 B)
+    static constexpr uint32_t SM_RNG = SM_HDR + 4096;       // 2 KB range descriptors (256 x 8 B)
+    static constexpr uint32_t SM_NATOFF = SM_RNG + 2048;    // index tables of the sweep (plan_host.h)
+    static constexpr uint32_t SM_LOCOFF = SM_NATOFF + PLAN_TABLE * 8;
+    static constexpr uint32_t SM_NATLOC = SM_LOCOFF + PLAN_TABLE * 8;
+    static constexpr uint32_t SM_ZOC = SM_NATLOC + PLAN_TABLE * 4;  // z bits of the staged terms outside the tile, packed against the tile number
+    static constexpr uint32_t SM_RED = SM_ZOC + CPLX_TERMS * 4;     // block reduction scratch
+    static constexpr uint32_t SM_TOTAL = SM_RED + NW * 16;
+};
+constexpr int SWEEP_MAX_GROUPS = 512;  // ranges per sweep <= 5 skip levels x 2 polarities x 3 kinds
+constexpr int BATCH_MAX_GROUPS = 128;
+// staged terms per sweep by tile size: real-coefficient sweeps are bounded by the kernel parameter, complex ones by shared memory
+inline int sweep_max_terms(int k, bool batch) {
+    const bool big = k >= PLAN_MAX_TILE_BITS;
+    if (batch) return big ? 1024 : 512;
+    return big ? SWEEP_CONST_TERMS : 1024;
+}
+static_assert((size_t)Geo<512>::NW * BATCH_MAX_GROUPS * 16 <= Geo<512>::REC_BYTES / 2 && (size_t)Geo<256>::NW * BATCH_MAX_GROUPS * 16 <= Geo<256>::REC_BYTES / 2,
+              "batch accumulators share the term area");
+static_assert(Geo<512>::SM_TOTAL <= 232448 - 1024, "exceeds the 227 KB of shared memory a CTA may use");
+static_assert(2 * (Geo<256>::SM_TOTAL + 1024) <= 232448, "two CTAs of 256 threads must fit one SM");
 
 __device__ __forceinline__ double2 block_reduce_sum(double2 v, double2* s_red) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -171,12 +185,12 @@ __device__ __forceinline__ void load_rec(const TermRec<float, true>* p, float& c
     zp = raw.z;
 }
 
-__device__ __forceinline__ uint32_t tile_word(uint32_t j) { return (j & (uint32_t)(R - 1)) * PLANE + (j >> RB); }
+template <uint32_t PL> __device__ __forceinline__ uint32_t tile_word(uint32_t j) { return (j & (uint32_t)(R - 1)) * PL + (j >> RB); }
 
 // partner of the thread's row r: word t ^ xt of plane r (pp points at it), or of plane r ^ xr when the X mask touches register rows
-template <bool XROW, typename cplx_t>
+template <bool XROW, uint32_t PL, typename cplx_t>
 __device__ __forceinline__ cplx_t partner_row(const cplx_t* __restrict__ pp, const uint32_t xr, const int r) {
-    return XROW ? pp[((uint32_t)r ^ xr) * PLANE] : pp[(uint32_t)r * PLANE];
+    return XROW ? pp[((uint32_t)r ^ xr) * PL] : pp[(uint32_t)r * PL];
 }
 
 // Where the staged terms of a sweep live.  Complex-coefficient sweeps keep them in shared memory (TermRec, signs flipped in place per
@@ -318,7 +332,7 @@ __device__ __forceinline__ void times_weight(real_t& sr, real_t& si, const real_
 }
 
 // <own| G |tile> of one group for the thread's 16 rows: sum_r conj(own_r) Wc(r) p_r with p_r the partner of row r.
-template <typename real_t, bool CPLX, int KIND>
+template <typename real_t, bool CPLX, int KIND, uint32_t PL>
 __device__ __forceinline__ void group_value_full(const typename CplxOf<real_t>::type* __restrict__ pp, const uint32_t xr, const Terms<real_t, CPLX>& terms,
                                                  const int tb, const int nt, const bool imag, const uint32_t jhi,
                                                  const typename CplxOf<real_t>::type (&own)[R], real_t& out_re, real_t& out_im) {
@@ -330,7 +344,7 @@ __device__ __forceinline__ void group_value_full(const typename CplxOf<real_t>::
         real_t a0 = (real_t)0, a1 = (real_t)0, b0 = (real_t)0, b1 = (real_t)0;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const cplx_t p = partner_row<(KIND & KIND_XROW) != 0>(pp, xr, r);
+            const cplx_t p = partner_row<(KIND & KIND_XROW) != 0, PL>(pp, xr, r);
             a0 = fma(own[r].x, p.x, a0);  // Re conj(own) p = a a' + b b'
             a1 = fma(own[r].y, p.y, a1);
             b0 = fma(own[r].x, p.y, b0);  // Im conj(own) p = a b' - b a'
@@ -349,7 +363,7 @@ __device__ __forceinline__ void group_value_full(const typename CplxOf<real_t>::
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const int r = 8 * ch + q;
-                const cplx_t p = partner_row<(KIND & KIND_XROW) != 0>(pp, xr, r);
+                const cplx_t p = partner_row<(KIND & KIND_XROW) != 0, PL>(pp, xr, r);
                 fr[q] = fma(own[r].x, p.x, own[r].y * p.y);
                 fi[q] = fma(own[r].x, p.y, -own[r].y * p.x);
             }
@@ -380,18 +394,19 @@ __device__ __forceinline__ void group_value_full(const typename CplxOf<real_t>::
 }
 
 // All groups of one range (same skip bit, polarity and kind) for the thread's 16 rows.
-template <typename real_t, bool CPLX, int MODE, int KIND>
+template <typename real_t, bool CPLX, int MODE, int KIND, uint32_t PL>
 __device__ __forceinline__ void process_range(const typename CplxOf<real_t>::type* __restrict__ tile, const Terms<real_t, CPLX>& terms,
                                               const uint2* __restrict__ s_hdr, double2* __restrict__ s_acc_warp, const int g0, const int g1, int tb,
                                               const uint32_t w0, const uint32_t jhi, const bool half,
                                               const typename CplxOf<real_t>::type (&own)[R], real_t (&acc_re)[R], real_t (&acc_im)[R],
                                               double& e_re, double& e_im) {
     using cplx_t = typename CplxOf<real_t>::type;
-    uint32_t hdr_next = s_hdr[g0].x;
+    constexpr bool PREFETCH = MODE == MODE_EXPECT;  // APPLY has no register to spare for it
+    uint32_t hdr_next = PREFETCH ? s_hdr[g0].x : 0u;
 #pragma unroll 1
     for (int g = g0; g < g1; ++g) {
-        const uint32_t hdr = hdr_next;
-        if (g + 1 < g1) hdr_next = s_hdr[g + 1].x;  // next group's header travels while this group is processed
+        const uint32_t hdr = PREFETCH ? hdr_next : s_hdr[g].x;
+        if (PREFETCH && g + 1 < g1) hdr_next = s_hdr[g + 1].x;  // next group's header travels while this group is processed
         const cplx_t* __restrict__ pp = tile + (w0 ^ ((hdr & HDR_XL_MASK) >> RB));  // partner thread's word of plane 0
         const uint32_t xr = hdr & (uint32_t)(R - 1);
         const int nt = (int)((hdr >> HDR_NT_SHIFT) & HDR_NT_MASK);
@@ -405,7 +420,7 @@ __device__ __forceinline__ void process_range(const typename CplxOf<real_t>::typ
                 real_t a0 = (real_t)0, a1 = (real_t)0, a2 = (real_t)0, a3 = (real_t)0;  // independent chains keep the FP64 pipe busy
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    const cplx_t p = partner_row<(KIND & KIND_XROW) != 0>(pp, xr, r);
+                    const cplx_t p = partner_row<(KIND & KIND_XROW) != 0, PL>(pp, xr, r);
                     if (r & 1) {
                         a2 = fma(own[r].x, p.x, a2);
                         a3 = fma(own[r].y, p.y, a3);
@@ -419,7 +434,7 @@ __device__ __forceinline__ void process_range(const typename CplxOf<real_t>::typ
                 real_t f[R];
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    const cplx_t p = partner_row<(KIND & KIND_XROW) != 0>(pp, xr, r);
+                    const cplx_t p = partner_row<(KIND & KIND_XROW) != 0, PL>(pp, xr, r);
                     f[r] = fma(own[r].x, p.x, own[r].y * p.y);
                 }
                 int t = tb;
@@ -439,7 +454,7 @@ __device__ __forceinline__ void process_range(const typename CplxOf<real_t>::typ
             }
         } else if (MODE == MODE_EXPECT || MODE == MODE_BATCH) {
             real_t sr, si;
-            group_value_full<real_t, CPLX, KIND>(pp, xr, terms, tb, nt, imag, jhi, own, sr, si);
+            group_value_full<real_t, CPLX, KIND, PL>(pp, xr, terms, tb, nt, imag, jhi, own, sr, si);
             if (MODE == MODE_EXPECT) {
                 e_re += (double)sr;
                 e_im += (double)si;
@@ -466,7 +481,7 @@ __device__ __forceinline__ void process_range(const typename CplxOf<real_t>::typ
                 const real_t wi = CPLX ? Sim : (imag ? Sre : (real_t)0);
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    const cplx_t p = partner_row<(KIND & KIND_XROW) != 0>(pp, xr, r);
+                    const cplx_t p = partner_row<(KIND & KIND_XROW) != 0, PL>(pp, xr, r);
                     if (CPLX) {
                         acc_re[r] += wr * p.x - wi * p.y;
                         acc_im[r] += wr * p.y + wi * p.x;
@@ -524,7 +539,7 @@ __device__ __forceinline__ void process_range(const typename CplxOf<real_t>::typ
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         const int r = 8 * ch + q;
-                        const cplx_t p = partner_row<(KIND & KIND_XROW) != 0>(pp, xr, r);
+                        const cplx_t p = partner_row<(KIND & KIND_XROW) != 0, PL>(pp, xr, r);
                         if (CPLX) {
                             acc_re[r] += W[q] * p.x - Wi[q] * p.y;
                             acc_im[r] += W[q] * p.y + Wi[q] * p.x;
@@ -548,7 +563,7 @@ __device__ __forceinline__ void process_range(const typename CplxOf<real_t>::typ
 template <typename real_t, bool CPLX>
 __device__ __forceinline__ void flip_signs(TermRec<real_t, CPLX>* __restrict__ s_rec, const uint32_t* __restrict__ s_zoc, const int nT, const uint32_t diff) {
     if (diff == 0) return;
-    for (int t = threadIdx.x; t < nT; t += NT) {
+    for (int t = threadIdx.x; t < nT; t += blockDim.x) {
         if (__popc(s_zoc[t] & diff) & 1) {
             s_rec[t].c = -s_rec[t].c;
             if constexpr (CPLX) s_rec[t].ci = -s_rec[t].ci;
@@ -564,24 +579,27 @@ __device__ __forceinline__ Terms<real_t, CPLX> make_terms(const SweepArgs& a, co
         return Terms<real_t, false>{a, tile};
 }
 
-template <typename real_t, bool CPLX, int MODE>
-__global__ void __launch_bounds__(NT, 1) tile_sweep_kernel(const __grid_constant__ SweepArgs a) {
+template <typename real_t, bool CPLX, int MODE, int NTH>
+__global__ void __launch_bounds__(NTH, NT_MAX / NTH) tile_sweep_kernel(const __grid_constant__ SweepArgs a) {
+    using G = Geo<NTH>;
+    constexpr int NT = NTH, NW = G::NW;
+    constexpr uint32_t PLANE = G::PLANE;
     using cplx_t = typename CplxOf<real_t>::type;
     using rec_t = TermRec<real_t, CPLX>;
     extern __shared__ __align__(16) unsigned char smem[];
     const int k = a.k;
     const uint32_t tile_amps = 1u << k;
     const int nT = a.n_terms, nG = a.n_groups, nR = a.n_ranges;
-    cplx_t* tile = reinterpret_cast<cplx_t*>(smem + SM_TILE);
-    rec_t* s_rec = reinterpret_cast<rec_t*>(smem + SM_REC);
-    uint2* s_hdr = reinterpret_cast<uint2*>(smem + SM_HDR);
-    uint2* s_rng = reinterpret_cast<uint2*>(smem + SM_RNG);
-    uint64_t* s_nat_off = reinterpret_cast<uint64_t*>(smem + SM_NATOFF);
-    uint64_t* s_loc_off = reinterpret_cast<uint64_t*>(smem + SM_LOCOFF);
-    uint32_t* s_nat_loc = reinterpret_cast<uint32_t*>(smem + SM_NATLOC);
-    uint32_t* s_zoc = reinterpret_cast<uint32_t*>(smem + SM_ZOC);
-    double2* s_acc = reinterpret_cast<double2*>(smem + SM_ACC);
-    double2* s_red = reinterpret_cast<double2*>(smem + SM_RED);
+    cplx_t* tile = reinterpret_cast<cplx_t*>(smem + G::SM_TILE);
+    rec_t* s_rec = reinterpret_cast<rec_t*>(smem + G::SM_REC);
+    uint2* s_hdr = reinterpret_cast<uint2*>(smem + G::SM_HDR);
+    uint2* s_rng = reinterpret_cast<uint2*>(smem + G::SM_RNG);
+    uint64_t* s_nat_off = reinterpret_cast<uint64_t*>(smem + G::SM_NATOFF);
+    uint64_t* s_loc_off = reinterpret_cast<uint64_t*>(smem + G::SM_LOCOFF);
+    uint32_t* s_nat_loc = reinterpret_cast<uint32_t*>(smem + G::SM_NATLOC);
+    uint32_t* s_zoc = reinterpret_cast<uint32_t*>(smem + G::SM_ZOC);
+    double2* s_acc = reinterpret_cast<double2*>(smem + G::SM_ACC);
+    double2* s_red = reinterpret_cast<double2*>(smem + G::SM_RED);
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const cplx_t* __restrict__ ket = reinterpret_cast<const cplx_t*>(a.ket);
@@ -606,6 +624,9 @@ __global__ void __launch_bounds__(NT, 1) tile_sweep_kernel(const __grid_constant
         }
     }
     unsigned long long prev_tile = 0;
+    __syncthreads();
+    const uint64_t off_lo = s_nat_off[tid & 127];
+    const uint32_t loc_lo = s_nat_loc[tid & 127];
     if (MODE == MODE_BATCH)
         for (int i = tid; i < NW * nG; i += NT) s_acc[i] = make_double2(0.0, 0.0);
 
@@ -632,22 +653,17 @@ __global__ void __launch_bounds__(NT, 1) tile_sweep_kernel(const __grid_constant
             // the tile is enumerated in natural order (consecutive threads = consecutive amplitudes of a 128 B segment) and
             // scattered to its tile-local words; a full tile is one batch of 16 independent 128-bit loads per thread
             if (tile_amps == R * NT) {
+                // idx = tid + u * NT: the low 7 index bits are the thread's own, looked up once (off_lo, loc_lo)
                 cplx_t v[R];
 #pragma unroll
-                for (int u = 0; u < R; ++u) {
-                    const uint32_t idx = tid + u * NT;
-                    v[u] = ld_stream(ket + (kbase | s_nat_off[idx & 127] | s_nat_off[128 + (idx >> 7)]));
-                }
+                for (int u = 0; u < R; ++u) v[u] = ld_stream(ket + (kbase | off_lo | s_nat_off[128 + ((tid + u * NT) >> 7)]));
                 if constexpr (CPLX) flip_signs<real_t, CPLX>(s_rec, s_zoc, nT, (uint32_t)(tile_id ^ prev_tile));  // shared memory only: overlaps the loads
 #pragma unroll
-                for (int u = 0; u < R; ++u) {
-                    const uint32_t idx = tid + u * NT;
-                    tile[tile_word(s_nat_loc[idx & 127] | s_nat_loc[128 + (idx >> 7)])] = v[u];
-                }
+                for (int u = 0; u < R; ++u) tile[tile_word<PLANE>(loc_lo | s_nat_loc[128 + ((tid + u * NT) >> 7)])] = v[u];
             } else {
                 if constexpr (CPLX) flip_signs<real_t, CPLX>(s_rec, s_zoc, nT, (uint32_t)(tile_id ^ prev_tile));
                 for (uint32_t idx = tid; idx < tile_amps; idx += NT)
-                    tile[tile_word(s_nat_loc[idx & 127] | s_nat_loc[128 + (idx >> 7)])] =
+                    tile[tile_word<PLANE>(s_nat_loc[idx & 127] | s_nat_loc[128 + (idx >> 7)])] =
                         ld_stream(ket + (kbase | s_nat_off[idx & 127] | s_nat_off[128 + (idx >> 7)]));
             }
             prev_tile = tile_id;
@@ -699,11 +715,11 @@ __global__ void __launch_bounds__(NT, 1) tile_sweep_kernel(const __grid_constant
                 const int g0 = (int)(d.x & 0xffffu), g1 = (int)(d.x >> 16), t0 = (int)(d.y & 0xffffu);
                 const uint32_t kind = (d.y >> RNG_KIND_SHIFT) & 3u;
                 if (kind == KIND_FAST)
-                    process_range<real_t, CPLX, MODE, KIND_FAST>(tile, terms, s_hdr, s_acc_warp, g0, g1, t0, w0, jhi, half, own, acc_re, acc_im, e_re, e_im);
+                    process_range<real_t, CPLX, MODE, KIND_FAST, PLANE>(tile, terms, s_hdr, s_acc_warp, g0, g1, t0, w0, jhi, half, own, acc_re, acc_im, e_re, e_im);
                 else if (kind == KIND_RUNS)
-                    process_range<real_t, CPLX, MODE, KIND_RUNS>(tile, terms, s_hdr, s_acc_warp, g0, g1, t0, w0, jhi, half, own, acc_re, acc_im, e_re, e_im);
+                    process_range<real_t, CPLX, MODE, KIND_RUNS, PLANE>(tile, terms, s_hdr, s_acc_warp, g0, g1, t0, w0, jhi, half, own, acc_re, acc_im, e_re, e_im);
                 else
-                    process_range<real_t, CPLX, MODE, KIND_RUNS | KIND_XROW>(tile, terms, s_hdr, s_acc_warp, g0, g1, t0, w0, jhi, half, own, acc_re, acc_im, e_re, e_im);
+                    process_range<real_t, CPLX, MODE, KIND_RUNS | KIND_XROW, PLANE>(tile, terms, s_hdr, s_acc_warp, g0, g1, t0, w0, jhi, half, own, acc_re, acc_im, e_re, e_im);
             }
             if (MODE == MODE_APPLY) {
 #pragma unroll
@@ -844,6 +860,7 @@ struct qfe_plan {
     PlanLimits lim;
     bool batch = false;
     bool force_direct = false;
+    bool hermitian = false;
     int device = 0;
     DevBuf g_hdr, r_desc, t_zl, t_zoc, t_cre, t_cim, d_x, d_z, d_cre, d_cim, dg_begin, nat_off, loc_off, nat_loc;
 };
@@ -863,26 +880,36 @@ static int find_class(const qfe_plan* p, int x_hi) {
     return -1;
 }
 
-static size_t sweep_smem_bytes(const SweepHost&, int, int, int, bool) { return SM_TOTAL; }
+// CTA size and grid of a sweep: 2^13-amplitude tiles = one CTA of 512 threads per SM, smaller tiles = two CTAs of 256 threads
+static int sweep_threads(int k) { return k >= PLAN_MAX_TILE_BITS ? NT_MAX : NT_MAX / 2; }
+static int sweep_grid(const qfe_ctx* ctx, const SweepHost& sw) {
+    return (int)std::min<int64_t>(sw.n_tiles, (int64_t)ctx->sm_count * (NT_MAX / sweep_threads(sw.k)));
+}
 
-template <typename real_t, bool CPLX, int MODE>
-static int launch_tile(qfe_ctx* ctx, const SweepArgs& args, int grid, size_t smem) {
-    auto kern = tile_sweep_kernel<real_t, CPLX, MODE>;
-    if (smem > 48 * 1024) QFE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, NT, smem, ctx->stream>>>(args);
+template <typename real_t, bool CPLX, int MODE, int NTH>
+static int launch_tile_n(qfe_ctx* ctx, const SweepArgs& args, int grid) {
+    auto kern = tile_sweep_kernel<real_t, CPLX, MODE, NTH>;
+    constexpr size_t smem = Geo<NTH>::SM_TOTAL;
+    QFE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, NTH, smem, ctx->stream>>>(args);
     ctx->launches++;
     QFE_CUDA(cudaGetLastError());
     return QFE_OK;
 }
 
+template <typename real_t, bool CPLX, int MODE>
+static int launch_tile(qfe_ctx* ctx, const SweepArgs& args, int grid) {
+    return sweep_threads(args.k) == NT_MAX ? launch_tile_n<real_t, CPLX, MODE, NT_MAX>(ctx, args, grid) : launch_tile_n<real_t, CPLX, MODE, NT_MAX / 2>(ctx, args, grid);
+}
+
 template <typename real_t, int MODE>
-static int launch_tile_c(qfe_ctx* ctx, const SweepArgs& args, int grid, size_t smem, bool cplx) {
-    return cplx ? launch_tile<real_t, true, MODE>(ctx, args, grid, smem) : launch_tile<real_t, false, MODE>(ctx, args, grid, smem);
+static int launch_tile_c(qfe_ctx* ctx, const SweepArgs& args, int grid, bool cplx) {
+    return cplx ? launch_tile<real_t, true, MODE>(ctx, args, grid) : launch_tile<real_t, false, MODE>(ctx, args, grid);
 }
 
 template <int MODE>
-static int launch_tile_d(qfe_ctx* ctx, const SweepArgs& args, int grid, size_t smem, bool cplx, int dtype) {
-    return dtype == QFE_C128 ? launch_tile_c<double, MODE>(ctx, args, grid, smem, cplx) : launch_tile_c<float, MODE>(ctx, args, grid, smem, cplx);
+static int launch_tile_d(qfe_ctx* ctx, const SweepArgs& args, int grid, bool cplx, int dtype) {
+    return dtype == QFE_C128 ? launch_tile_c<double, MODE>(ctx, args, grid, cplx) : launch_tile_c<float, MODE>(ctx, args, grid, cplx);
 }
 
 template <int MODE>
@@ -961,7 +988,7 @@ static int run_class_reduce(qfe_ctx* ctx, const qfe_plan* p, int ci, const void*
         size_t max_partials = 1;
         for (int si = cls.sweep_begin; si < cls.sweep_end; ++si) {
             const SweepHost& sw = p->h.sweeps[si];
-            const size_t grid = (size_t)std::min<int64_t>(sw.n_tiles, ctx->sm_count);
+            const size_t grid = (size_t)sweep_grid(ctx, sw);
             max_partials = std::max(max_partials, grid * (size_t)(batch ? sw.group_end - sw.group_begin : 1));
         }
         QFE_TRY(ctx->partials.reserve(sizeof(double2) * max_partials));
@@ -973,14 +1000,13 @@ static int run_class_reduce(qfe_ctx* ctx, const qfe_plan* p, int ci, const void*
             a.ket = ket;
             a.bra = bra;
             a.same_tile = (bra == ket && sw.ket_xor == 0) ? 1 : 0;
-            const int grid = (int)std::min<int64_t>(sw.n_tiles, ctx->sm_count);
+            const int grid = sweep_grid(ctx, sw);
             const int n_ranges = batch ? a.n_groups : 1;
             a.partials = ctx->partials.as<double2>();
-            const size_t smem = sweep_smem_bytes(sw, a.n_terms, a.n_groups, dtype, batch);
             if (batch)
-                QFE_TRY(launch_tile_d<MODE_BATCH>(ctx, a, grid, smem, sw.complex_w, dtype));
+                QFE_TRY(launch_tile_d<MODE_BATCH>(ctx, a, grid, sw.complex_w, dtype));
             else
-                QFE_TRY(launch_tile_d<MODE_EXPECT>(ctx, a, grid, smem, sw.complex_w, dtype));
+                QFE_TRY(launch_tile_d<MODE_EXPECT>(ctx, a, grid, sw.complex_w, dtype));
             reduce_partials<<<(n_ranges + 3) / 4, 128, 0, s>>>(a.partials, n_ranges, grid, d_vals + vpos);
             ctx->launches++;
             QFE_CUDA(cudaGetLastError());
@@ -1045,16 +1071,15 @@ int qfe_plan_create(qfe_ctx* ctx, const qfe_terms* t, int n_local, int shard, in
     const char* fd = getenv("QFE_FORCE_DIRECT");
     p->force_direct = (tile_bits < 0) || (fd && fd[0] == '1');
     PlanLimits lim;
-    lim.tile_bits = tile_bits > 0 ? tile_bits : 13;
+    const char* tb_env = getenv("QFE_TILE_BITS");  // development: default tile size without touching the callers
+    lim.tile_bits = tile_bits > 0 ? tile_bits : (tb_env && atoi(tb_env) > 0 ? atoi(tb_env) : 13);
     if (lim.tile_bits > 13) lim.tile_bits = 13;  // 2^13 complex128 amplitudes = 128 KB of the 227 KB shared memory
-    if (p->batch) {
-        lim.max_terms = BATCH_MAX_TERMS;
-        lim.max_groups = BATCH_MAX_GROUPS;
-    } else {
-        lim.max_terms = SWEEP_MAX_TERMS;
-        lim.max_groups = SWEEP_MAX_GROUPS;
-    }
+    lim.max_terms = sweep_max_terms(std::min(n_local, lim.tile_bits), p->batch);
+    lim.max_groups = p->batch ? BATCH_MAX_GROUPS : SWEEP_MAX_GROUPS;
     p->lim = lim;
+    p->hermitian = true;
+    for (int64_t i = 0; i < t->T && p->hermitian; ++i) p->hermitian = t->c[2 * i + 1] == 0.0;
+    for (int64_t i = 0; i < t->n_slots && p->hermitian; ++i) p->hermitian = t->constant[2 * i + 1] == 0.0;
     TermView v;
     v.n = t->n;
     v.T = t->T;
@@ -1093,6 +1118,33 @@ int qfe_plan_info(const qfe_plan* p, int64_t* n_sweeps, int64_t* n_groups, int64
     if (n_terms) *n_terms = (int64_t)p->h.d_x.size();
     if (n_classes) *n_classes = (int32_t)p->h.classes.size();
     if (tile_bits) *tile_bits = tiles ? p->h.k : 0;
+    return QFE_OK;
+}
+
+int qfe_plan_hermitian(const qfe_plan* p, int* hermitian) {
+    QFE_REQUIRE(p && hermitian, QFE_ERR_ARG, "null argument");
+    *hermitian = p->hermitian ? 1 : 0;
+    return QFE_OK;
+}
+
+int qfe_plan_work(const qfe_plan* p, int64_t* half_groups, int64_t* full_groups, int64_t* half_terms, int64_t* full_terms) {
+    QFE_REQUIRE(p, QFE_ERR_ARG, "null plan");
+    int64_t hg = 0, fg = 0, ht = 0, ft = 0;
+    const PlanHost& h = p->h;
+    for (const SweepHost& s : h.sweeps)
+        for (int r = s.range_begin; r < s.range_end; ++r) {
+            const uint32_t d0 = h.r_desc[2 * r], d1 = h.r_desc[2 * r + 1];
+            const bool half = (d1 >> RNG_SKIP_SHIFT) != 0;
+            for (uint32_t g = (d0 & 0xffffu); g < (d0 >> 16); ++g) {
+                const int64_t nt = (h.g_hdr[2 * (s.group_begin + g)] >> HDR_NT_SHIFT) & HDR_NT_MASK;
+                (half ? hg : fg) += 1;
+                (half ? ht : ft) += nt;
+            }
+        }
+    if (half_groups) *half_groups = hg;
+    if (full_groups) *full_groups = fg;
+    if (half_terms) *half_terms = ht;
+    if (full_terms) *full_terms = ft;
     return QFE_OK;
 }
 
@@ -1181,8 +1233,7 @@ int qfe_apply_class(qfe_ctx* ctx, const qfe_plan* p, int x_hi, const void* ket, 
             a.out_vec = y;
             a.same_tile = 0;
             a.accumulate = (si == cls.sweep_begin) ? (accumulate ? 1 : 0) : 1;
-            const int grid = (int)std::min<int64_t>(sw.n_tiles, ctx->sm_count);
-            QFE_TRY(launch_tile_d<MODE_APPLY>(ctx, a, grid, sweep_smem_bytes(sw, a.n_terms, a.n_groups, dtype, false), sw.complex_w, dtype));
+            QFE_TRY(launch_tile_d<MODE_APPLY>(ctx, a, sweep_grid(ctx, sw), sw.complex_w, dtype));
         }
     } else {
         DirectArgs a;

@@ -55,6 +55,13 @@ class Plan:
         cls = np.zeros(max(self.n_classes, 1), dtype=np.int32)
         check(engine.lib.qfe_plan_classes(h, as_ptr(cls, C.c_int32), len(cls)))
         self.classes = [int(v) for v in cls[: self.n_classes]]
+        herm = C.c_int()
+        check(engine.lib.qfe_plan_hermitian(h, C.byref(herm)))
+        self.hermitian = bool(herm.value)  # all coefficients real: every x_hi class is a Hermitian operator
+        w = [C.c_int64() for _ in range(4)]
+        check(engine.lib.qfe_plan_work(h, *[C.byref(v) for v in w]))
+        # groups of the tiled layout visited on half / all rows of a tile in <psi|H|psi>, and their staged terms
+        self.half_groups, self.full_groups, self.half_terms, self.full_terms = (v.value for v in w)
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -354,6 +361,92 @@ class Engine:
         self._sync_torch()
         check(self.lib.qfe_vec_product_state(self.ctx, C.c_void_p(psi.data_ptr()), n_local, shard, nqbits, as_ptr(ab.view(np.float64), C.c_double), _dtype_code(psi)))
         return psi
+
+    def basis_state(self, nqbits: int, index: int, dtype=None, n_local: int | None = None, shard: int = 0):
+        """|index> with qubit 0 = most significant bit (e.g. the Hartree-Fock determinant: the first n_e qubits set)."""
+        torch = _torch()
+        dtype = dtype or torch.complex128
+        n_local = nqbits if n_local is None else n_local
+        N = 1 << n_local
+        local = index - shard * N
+        psi = torch.empty(N, dtype=dtype, device=f"cuda:{self.device}")
+        self._sync_torch()
+        check(self.lib.qfe_vec_basis_state(self.ctx, C.c_void_p(psi.data_ptr()), N, _dtype_code(psi), local if 0 <= local < N else -1))
+        return psi
+
+    # ---- state evolution (SURVEY 8f rank 3) ----------------------------------------------------
+    def pauli_rotations(self, psi, x, z, theta) -> None:
+        """In place psi <- exp(-i theta[K-1] P[K-1]) ... exp(-i theta[0] P[0]) psi with P[k] = i^{|x&z|} X^x Z^z (packed masks,
+        bit n-1-q <-> qubit q).  Consecutive rotations on nearby qubits are fused into one pass over the state."""
+        nqbits = int(psi.numel()).bit_length() - 1
+        x = np.ascontiguousarray(x, dtype=np.uint64)
+        z = np.ascontiguousarray(z, dtype=np.uint64)
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        if not (len(x) == len(z) == len(theta)):
+            raise ValueError("x, z and theta must have the same length")
+        self._check_state(psi, 1 << nqbits)
+        self._sync_torch()
+        check(self.lib.qfe_pauli_rotations(self.ctx, nqbits, len(x), as_ptr(x, C.c_uint64), as_ptr(z, C.c_uint64), as_ptr(theta, C.c_double),
+                                           C.c_void_p(psi.data_ptr()), _dtype_code(psi)))
+
+    def trotter_slice(self, hamiltonian, psi, coeff: float = 1.0, n_steps: int = 1) -> None:
+        """In place first-order Trotter slice(s) prod_t exp(-i coeff Re(c_t) P_t) in the term order of ``hamiltonian``, the first
+        term applied first: what make_spin_hamiltonian_trotter_slice(hamiltonian, coeff) builds as a circuit
+        (/root/reference/qat/fermion/trotterisation.py:85-150).  ``hamiltonian``: a SpinHamiltonian or PackedTerms."""
+        from .packed import PackedTerms, pack_terms
+
+        if isinstance(hamiltonian, PackedTerms):
+            x, z, c, _, _ = hamiltonian.arrays()
+        else:
+            x, z, c = pack_terms(hamiltonian.nbqbits, hamiltonian.terms)[:3]
+        theta = coeff * np.real(np.asarray(c))
+        for _ in range(n_steps):
+            self.pauli_rotations(psi, x, z, theta)
+
+    def evolve_operators(self, psi, operators, thetas) -> None:
+        """In place psi <- prod_k exp(-i theta_k O_k) psi, first operator first, each exp(-i theta O) factorised term by term as
+        prod_t exp(-i theta Re(c_t) P_t) in the term order of O: the parameterised Trotter slices AdaptVQEPlugin._grow_ansatz appends
+        per selected pool operator (/root/reference/qat/plugins/adapt_vqe.py:64-141; like the reference only the real part of a
+        coefficient is used).  ``operators``: Hermitian SpinHamiltonians, e.g. the cluster operators of get_cluster_ops
+        (/root/reference/qat/fermion/chemistry/ucc.py:801-852) mapped to spins."""
+        from .packed import pack_terms
+
+        xs, zs, th = [], [], []
+        for op, theta in zip(operators, thetas):
+            x, z, c = pack_terms(op.nbqbits, op.terms)[:3]
+            xs.append(np.asarray(x, dtype=np.uint64))
+            zs.append(np.asarray(z, dtype=np.uint64))
+            th.append(float(theta) * np.real(np.asarray(c)))
+        if xs:
+            self.pauli_rotations(psi, np.concatenate(xs), np.concatenate(zs), np.concatenate(th))
+
+    # ---- overlaps (SURVEY 8f ranks 1 and 2) ------------------------------------------------------
+    def gram(self, bras, kets=None) -> np.ndarray:
+        """G[i, j] = <bras[i]|kets[j]> (kets = bras: Hermitian, only the upper triangle is computed)."""
+        same = kets is None
+        kets = bras if same else kets
+        g = np.zeros((len(bras), len(kets)), dtype=np.complex128)
+        for i, b in enumerate(bras):
+            for j, k in enumerate(kets):
+                if same and j < i:
+                    g[i, j] = np.conj(g[j, i])
+                else:
+                    g[i, j] = self.dot(b, k)
+        return g
+
+    def qfim(self, dpsis, psi) -> np.ndarray:
+        """Quantum Fisher information matrix g_kl = 4 Re(<d_k psi|d_l psi> - <d_k psi|psi><psi|d_l psi>) from the derivative states,
+        the quantity GradientDescentOptimizer assembles from Hadamard-test circuits
+        (/root/reference/qat/plugins/qfim_plugin.py:159-199)."""
+        g = self.gram(dpsis)
+        b = np.array([self.dot(d, psi) for d in dpsis])  # <d_k psi|psi>
+        return 4.0 * np.real(g - np.outer(b, np.conj(b)))
+
+    def energy_gradient(self, terms_or_plan, dpsis, psi) -> np.ndarray:
+        """dE/dtheta_k = 2 Re <d_k psi|H|psi> (/root/reference/qat/fermion/auto_derivatives.py:473-551 evaluates the same number
+        term by term through ancilla circuits)."""
+        phi = self.apply(terms_or_plan, psi)
+        return np.array([2.0 * self.dot(d, phi).real for d in dpsis])
 
     def dot(self, a, b) -> complex:
         out = np.zeros(2, dtype=np.float64)

@@ -12,6 +12,8 @@ observable evaluations are done by libqfe.
                                                                  (adapt_vqe.py:50-62, 181-195)
 * ``SeqOptim.optimize``                                      <->  SeqOptim.optimize (sequential_optimization.py:104-146)
 * ``vqe_energy``                                             <->  VQE.fun (vqe.py:53-59)
+* ``qse_matrices``                                           <->  the H / S loops of the QSE helper (chemistry/qse.py:191-214)
+* ``GradientDescentOptimizer``                               <->  GradientDescentOptimizer.optimize (naturalgradient/qfim_plugin.py:96-251)
 """
 
 from __future__ import annotations
@@ -169,3 +171,91 @@ def vqe_energy(hamiltonian: SpinHamiltonian, state_routine: Callable, engine=Non
         return eng.energy(plan, state_routine(theta))
 
     return fun
+
+
+def qse_matrices(hamiltonian: SpinHamiltonian, psi, expansion_operators: Sequence[SpinHamiltonian], engine=None, threshold: float = 1e-15):
+    """Quantum-subspace-expansion matrices H_ij = <psi|O_i^dag H O_j|psi>, S_ij = <psi|O_i^dag O_j|psi>
+    (/root/reference/qat/fermion/chemistry/qse.py:191-214: the reference expands O_i^dag H O_j as an observable and submits dim^2 jobs
+    per matrix).  Here phi_j = O_j|psi> and H|phi_j> are formed on the device once per j and the matrices are overlaps.  Returns real
+    matrices with entries below ``threshold`` in modulus set to zero, like the reference."""
+    from .engine import get_engine
+
+    eng = engine or get_engine()
+    h_plan = eng.plan(hamiltonian.packed(eng))
+    phis = [eng.apply(eng.plan(op.packed(eng)), psi) for op in expansion_operators]
+    dim = len(phis)
+    matrix_h = np.zeros((dim, dim), dtype=np.float64)
+    matrix_s = np.zeros((dim, dim), dtype=np.float64)
+    for j in range(dim):
+        chi = eng.apply(h_plan, phis[j])
+        for i in range(dim):
+            sh = eng.dot(phis[i], chi)
+            ss = eng.dot(phis[i], phis[j])
+            matrix_h[i, j] = sh.real if abs(sh) > threshold else 0.0
+            matrix_s[i, j] = ss.real if abs(ss) > threshold else 0.0
+    return matrix_h, matrix_s
+
+
+class GradientDescentOptimizer:
+    """``GradientDescentOptimizer.optimize`` (/root/reference/qat/fermion/naturalgradient/qfim_plugin.py:96-251) with the ancilla
+    circuits replaced by overlaps of device states: theta <- theta - lambda_step * g^+ grad E, g the quantum Fisher information
+    metric (natural gradient) or the identity.  ``state_and_derivatives(theta) -> (psi, [d psi / d theta_k])`` supplies the state
+    and its parameter derivatives (state preparation is outside this path; ``Engine.pauli_rotations`` can build them)."""
+
+    def __init__(self, maxiter: int = 1000, natural_gradient: bool = True, lambda_step: float = 0.2, stop_crit: str = "grad_norm",
+                 tol: float = 1e-10, x0=None, engine=None):
+        if stop_crit not in ("grad_norm", "energy_dist", "none"):
+            raise ValueError(f"unknown stopping criterion {stop_crit}")
+        self.maxiter = maxiter
+        self.natural_gradient = natural_gradient
+        self.lambda_step = lambda_step
+        self.stop_crit = stop_crit
+        self.tolerance = tol
+        self.initial_parameters = None if x0 is None else np.array(x0, dtype=float)
+        self.engine = engine
+        self.trace: List[float] = []
+        self.iterations = 0
+        self.check_crit_val = None
+
+    def optimize(self, var_names: Sequence[str], hamiltonian: SpinHamiltonian, state_and_derivatives: Callable):
+        from .engine import get_engine
+
+        eng = self.engine or get_engine()
+        plan = eng.plan(hamiltonian.packed(eng))
+        n_par = len(var_names)
+        if self.initial_parameters is None:
+            self.initial_parameters = np.random.uniform(0, 2 * np.pi, n_par)
+        if len(self.initial_parameters) != n_par:
+            raise ValueError(f"Initial parameters ({len(self.initial_parameters)}) do not match the job parameter names {list(var_names)}")
+        cur_params = np.array(self.initial_parameters, dtype=float)
+        angles = [list(cur_params)]
+        psi, dpsis = state_and_derivatives(cur_params)
+        energy = eng.energy(plan, psi)
+        self.trace = [energy]
+        self.iterations = 0
+        stopping = False
+        while self.iterations < self.maxiter and not stopping:
+            cur_grad = eng.energy_gradient(plan, dpsis, psi)
+            cur_grad = np.real(np.where(np.abs(cur_grad) < 1e-10, 0.0, cur_grad))
+            if self.natural_gradient:
+                qfim = eng.qfim(dpsis, psi)
+                qfim[np.abs(qfim) < 1e-10] = 0
+                try:
+                    cur_params = np.real(cur_params + np.linalg.solve(qfim, -self.lambda_step * cur_grad))
+                except np.linalg.LinAlgError:
+                    cur_params = np.real(cur_params - self.lambda_step * np.linalg.pinv(qfim).dot(cur_grad))
+            else:
+                cur_params = np.real(cur_params - self.lambda_step * cur_grad)
+            angles.append(list(cur_params))
+            psi, dpsis = state_and_derivatives(cur_params)
+            energy = eng.energy(plan, psi)
+            if self.stop_crit == "energy_dist" and self.iterations > 0:
+                self.check_crit_val = abs(energy - self.trace[-1])
+            self.trace.append(energy)
+            if self.stop_crit == "grad_norm":
+                self.check_crit_val = float(np.linalg.norm(cur_grad))
+            if self.stop_crit != "none" and self.check_crit_val is not None and self.check_crit_val < self.tolerance:
+                stopping = True
+            self.iterations += 1
+        angle_energy = [(angles[i], self.trace[i]) for i in range(len(self.trace))]
+        return self.trace[-1], list(cur_params), {"iterations": self.iterations, "energies": angle_energy}

@@ -46,7 +46,8 @@ class CpuBackend:
         classes = set((terms.x >> np.uint64(n_local)).tolist()) if n_local < 64 else {0}
         if np.any(terms.constant != 0):
             classes.add(0)
-        return SimpleNamespace(terms=terms, nqbits=terms.nqbits, n_local=n_local, shard=shard, classes=sorted(int(v) for v in classes))
+        hermitian = bool(np.all(terms.c.imag == 0) and np.all(terms.constant.imag == 0))
+        return SimpleNamespace(terms=terms, nqbits=terms.nqbits, n_local=n_local, shard=shard, classes=sorted(int(v) for v in classes), hermitian=hermitian)
 
     def _run(self, plan, x_hi, bra, ket):
         t = plan.terms

@@ -1,0 +1,227 @@
+"""SURVEY 8(f) rows on the B200 (-m gpu): basis states and fused Pauli rotations (Trotter slices, ansatz layers), overlap / QFIM /
+energy-gradient evaluation, QSE matrices and the natural-gradient optimizer, each against oracle/evolve.py.  Tolerances as for the
+hot path: 1e-10 relative in complex128, 1e-5 in complex64."""
+
+import numpy as np
+import pytest
+
+from oracle import evolve, models, spin, transforms
+
+pytestmark = pytest.mark.gpu
+
+RTOL64, RTOL32 = 1e-10, 1e-5
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import myqlm_fermion_b200 as qfe
+
+    return qfe.get_engine(0)
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+def _state(n, seed=0):
+    rng = np.random.default_rng(seed)
+    psi = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)
+    return psi / np.linalg.norm(psi)
+
+
+def _dev(a):
+    return _torch().from_numpy(np.ascontiguousarray(a)).to("cuda:0")
+
+
+def test_basis_state(eng):
+    for n, idx in ((1, 1), (5, 19), (12, 0), (12, 4095)):
+        psi = eng.basis_state(n, idx).cpu().numpy()
+        want = np.zeros(1 << n, dtype=np.complex128)
+        want[idx] = 1
+        assert np.array_equal(psi, want)
+    # a shard that does not hold the occupied amplitude is all zero; the one that does holds it at its local index
+    assert not eng.basis_state(6, 40, n_local=4, shard=1).cpu().numpy().any()
+    assert eng.basis_state(6, 40, n_local=4, shard=2).cpu().numpy()[8] == 1
+    assert eng.basis_state(4, 3, dtype=_torch().complex64).dtype == _torch().complex64
+
+
+@pytest.mark.parametrize("n", [3, 9, 13, 15])
+def test_random_rotations_match_the_oracle(eng, n):
+    """Arbitrary X/Z masks (diagonal ones included), many more rotations than one fused batch can hold when n > 13."""
+    rng = np.random.default_rng(n)
+    K = 60
+    x = rng.integers(0, 1 << n, size=K, dtype=np.uint64)
+    if n > 13:  # a rotation may flip at most 10 qubits besides the tile's low bits
+        keep = rng.integers(0, 1 << n, size=K, dtype=np.uint64) & rng.integers(0, 1 << n, size=K, dtype=np.uint64)
+        x &= keep
+    x[::7] = 0
+    z = rng.integers(0, 1 << n, size=K, dtype=np.uint64)
+    theta = rng.uniform(-np.pi, np.pi, size=K)
+    psi = _state(n, 1)
+    want = evolve.rotations(n, x, z, theta, psi)
+    d = _dev(psi)
+    eng.pauli_rotations(d, x, z, theta)
+    got = d.cpu().numpy()
+    assert np.max(np.abs(got - want)) <= RTOL64 * np.max(np.abs(want))
+    d32 = _dev(psi.astype(np.complex64))
+    eng.pauli_rotations(d32, x, z, theta)
+    assert np.max(np.abs(d32.cpu().numpy() - want)) <= RTOL32 * np.max(np.abs(want)) * 10
+
+
+def test_rotation_argument_errors(eng):
+    import myqlm_fermion_b200 as qfe
+
+    d = _dev(_state(15, 0))
+    with pytest.raises(qfe.QfeError):  # flips 14 qubits: wider than a tile
+        eng.pauli_rotations(d, [(1 << 14) - 1 << 1], [0], [0.1])
+    with pytest.raises(qfe.QfeError):  # acts outside the register
+        eng.pauli_rotations(d, [1 << 20], [0], [0.1])
+    with pytest.raises(ValueError):
+        eng.pauli_rotations(d, [1, 2], [0], [0.1])
+
+
+def test_trotter_slice_of_a_hubbard_chain(eng):
+    """make_spin_hamiltonian_trotter_slice semantics: term order of the Hamiltonian, theta_t = coeff * Re c_t; many steps of a small
+    step approach exp(-i t H) (first-order Trotter error, checked loosely) while one slice matches the oracle to rounding."""
+    import myqlm_fermion_b200 as qfe
+
+    t_mat = np.zeros((3, 3))
+    for i in range(2):
+        t_mat[i, i + 1] = t_mat[i + 1, i] = -1.0
+    hs = qfe.make_hubbard_model(t_mat, 4.0, 2.0).to_spin("jordan-wigner")
+    n = hs.nbqbits
+    x, z, c = qfe.pack_terms(n, hs.terms)
+    psi = _state(n, 3)
+    d = _dev(psi)
+    eng.trotter_slice(hs, d, coeff=0.21)
+    want = evolve.trotter_slice(n, x, z, c, 0.21, psi)
+    assert np.max(np.abs(d.cpu().numpy() - want)) <= RTOL64
+    # gate-level restatement of the reference circuit on the same term list
+    want_gates = evolve.trotter_slice_circuit(n, [(t.coeff, t.op, t.qbits) for t in hs.terms], 0.21, psi)
+    assert np.max(np.abs(d.cpu().numpy() - want_gates)) <= 1e-10
+    import scipy.linalg
+
+    hm = spin.csr_from_packed(n, x, z, c, hs.constant_coeff).toarray()
+    d = _dev(psi)
+    steps, total = 400, 0.5
+    eng.trotter_slice(hs, d, coeff=total / steps, n_steps=steps)
+    exact = scipy.linalg.expm(-1j * total * (hm - hs.constant_coeff * np.eye(1 << n))) @ psi
+    assert np.max(np.abs(d.cpu().numpy() - exact)) < 2e-2
+    assert abs(np.linalg.norm(d.cpu().numpy()) - 1) < 1e-12
+
+
+def test_uccsd_layer_from_the_hartree_fock_state(eng):
+    """prod_k exp(-i theta_k tau_k)|HF> with tau_k the (Hermitian) UCCSD cluster operators in JW form, as
+    AdaptVQEPlugin._grow_ansatz builds it (adapt_vqe.py:64-141).  The strings of one cluster operator commute, so each factor is
+    the exact exponential: compared with dense expm."""
+    import scipy.linalg
+
+    import myqlm_fermion_b200 as qfe
+
+    n, n_e = 8, 4
+    pool_terms = models.cluster_ops(n_e, n)[:6]
+    pool = [transforms.transform(n, op, 0.0, "jordan-wigner").canonical() for op in pool_terms]
+    ops = []
+    for px, pz, pc, pk in pool:
+        assert np.max(np.abs(np.imag(pc))) < 1e-14  # Hermitian: real Pauli coefficients
+        terms = []
+        for xx, zz, cc in zip(px, pz, pc):
+            op, qb = qfe.unpack_term(n, int(xx), int(zz))
+            terms.append(qfe.Term(complex(cc), op, qb))
+        ops.append(qfe.SpinHamiltonian(n, terms))
+    thetas = np.linspace(0.1, 0.6, len(ops))
+    hf = models.hf_ket(n_e, n)
+    psi = eng.basis_state(n, hf)
+    eng.evolve_operators(psi, ops, thetas)
+    want = np.zeros(1 << n, dtype=np.complex128)
+    want[hf] = 1
+    for (px, pz, pc, pk), th in zip(pool, thetas):
+        want = scipy.linalg.expm(-1j * th * spin.csr_from_packed(n, px, pz, pc, pk).toarray()) @ want
+    assert np.max(np.abs(psi.cpu().numpy() - want)) <= 1e-10
+    assert abs(np.linalg.norm(psi.cpu().numpy()) - 1) < 1e-12
+
+
+def test_gram_qfim_and_energy_gradient(eng):
+    n, P = 10, 5
+    states = [_state(n, 10 + k) for k in range(P)]
+    psi = _state(n, 99)
+    d_states = [_dev(s) for s in states]
+    d_psi = _dev(psi)
+    g = eng.gram(d_states)
+    want_g = np.array(states).conj() @ np.array(states).T
+    assert np.max(np.abs(g - want_g)) <= 1e-12
+    g2 = eng.gram(d_states[:2], d_states[2:])
+    assert np.max(np.abs(g2 - want_g[:2, 2:])) <= 1e-12
+    assert np.max(np.abs(eng.qfim(d_states, d_psi) - evolve.qfim(states, psi))) <= 1e-11
+    one, two = models.synthetic_integrals(5, seed=7)
+    hpq, hpqrs = models.convert_to_h_integrals(one, two)
+    terms = eng.terms_from_integrals(hpq, hpqrs)
+    x, z, c, _, k = terms.arrays()
+    phi = spin.apply_packed(n, x, z, c, complex(k[0]), psi)
+    want_grad = np.array([2 * np.vdot(s, phi).real for s in states])
+    got_grad = eng.energy_gradient(terms, d_states, d_psi)
+    assert np.max(np.abs(got_grad - want_grad)) <= RTOL64 * np.max(np.abs(want_grad))
+
+
+def test_qse_matrices(eng):
+    """qse.py:191-214 on the 2x2 Hubbard plaquette ground state region: H and S from device overlaps vs the dense definition."""
+    import myqlm_fermion_b200 as qfe
+
+    n = 6
+    t_mat = np.zeros((3, 3))
+    for i in range(2):
+        t_mat[i, i + 1] = t_mat[i + 1, i] = -1.0
+    hs = qfe.make_hubbard_model(t_mat, 2.0, 1.0).to_spin("jordan-wigner")
+    ops = [
+        qfe.SpinHamiltonian(n, [], constant_coeff=1.0),
+        qfe.SpinHamiltonian(n, [qfe.Term(1.0, "XX", [0, 2]), qfe.Term(0.5, "YY", [0, 2])]),
+        qfe.SpinHamiltonian(n, [qfe.Term(1.0, "Z", [1]), qfe.Term(-0.25j, "XY", [3, 5])]),
+    ]
+    psi = _state(n, 5)
+    mh, ms = qfe.plugins.qse_matrices(hs, _dev(psi), ops, engine=eng)
+    hx, hz, hc, hk = hs.packed_arrays()
+    packed_ops = [o.packed_arrays() for o in ops]
+    want_h, want_s = evolve.qse_matrices(n, (hx, hz, hc, hk), packed_ops, psi)
+    assert np.max(np.abs(mh - want_h)) <= 1e-11 and np.max(np.abs(ms - want_s)) <= 1e-12
+
+
+@pytest.mark.parametrize("natural", [True, False])
+def test_gradient_descent_optimizer_follows_the_reference_update(eng, natural):
+    """Two-parameter ansatz exp(-i t1 Y0) exp(-i t0 Y1 X0)|00> on H = XX + YY + ZZ (the Hamiltonian of the reference's natural
+    gradient test, tests/integration/test_integration_natural_gradient_plugin.py:30): same trajectory as the dense restatement of
+    GradientDescentOptimizer.optimize, and the energy decreases."""
+    import myqlm_fermion_b200 as qfe
+
+    n = 2
+    hs = qfe.SpinHamiltonian(n, [qfe.Term(1, op, [0, 1]) for op in ["XX", "YY", "ZZ"]])
+    gx, gz, _ = qfe.pack_terms(n, [qfe.Term(1, "XY", [0, 1]), qfe.Term(1, "Y", [0])])
+
+    def dense(params):
+        psi0 = np.zeros(4, dtype=np.complex128)
+        psi0[0] = 1
+        a = evolve.rotate(n, int(gx[0]), int(gz[0]), params[0], psi0)
+        psi = evolve.rotate(n, int(gx[1]), int(gz[1]), params[1], a)
+        # d/dt exp(-i t P) = -i P exp(-i t P)
+        d0 = evolve.rotate(n, int(gx[1]), int(gz[1]), params[1], -1j * spin.apply_packed(n, [gx[0]], [gz[0]], [1.0], 0.0, a))
+        d1 = -1j * spin.apply_packed(n, [gx[1]], [gz[1]], [1.0], 0.0, psi)
+        return psi, [d0, d1]
+
+    def device(params):
+        psi, dps = dense(params)  # derivative states are supplied by the state-preparation side
+        check = eng.basis_state(n, 0)
+        eng.pauli_rotations(check, gx, gz, params)
+        assert np.max(np.abs(check.cpu().numpy() - psi)) < 1e-12
+        return check, [_dev(d) for d in dps]
+
+    x0 = [0.3, -0.4]
+    hx, hz, hc, hk = hs.packed_arrays()
+    hm = spin.csr_from_packed(n, hx, hz, hc, hk).toarray()
+    want_e, want_p, want_trace = evolve.gradient_descent(hm, dense, x0, maxiter=25, natural_gradient=natural, lambda_step=0.2, tol=1e-10)
+    opt = qfe.plugins.GradientDescentOptimizer(maxiter=25, natural_gradient=natural, lambda_step=0.2, tol=1e-10, x0=x0, engine=eng)
+    e, p, info = opt.optimize(["t0", "t1"], hs, device)
+    assert info["iterations"] == len(want_trace) - 1
+    assert np.max(np.abs(np.array(opt.trace) - np.array(want_trace))) <= 1e-9
+    assert np.max(np.abs(np.array(p) - want_p)) <= 1e-8
+    assert e < opt.trace[0] - 0.1
