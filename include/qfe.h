@@ -121,6 +121,10 @@ int qfe_plan_destroy(qfe_plan* p);
  * ``out`` (host) has 2*n_slots doubles and is OVERWRITTEN.  For a single-slot set this is the
  * class's share of <bra|H|ket>; the constant contributes constant*<bra|ket> in class 0.        */
 int qfe_expectation_class(qfe_ctx* ctx, const qfe_plan* p, int x_hi, const void* bra, const void* ket, int dtype, double* out);
+/* the same restricted to every n_parts-th sweep of the class, starting with sweep `part`: the n_parts calls add up to
+ * qfe_expectation_class.  Two ranks that hold the shards r and r^x_hi of a Hermitian operator each evaluate one half (their own shard
+ * as the bra) and count it twice: <psi_r|G|psi_r'> + <psi_r'|G|psi_r> = 2 Re <psi_r|G_A|psi_r'> + 2 Re <psi_r'|G_B|psi_r>, G = G_A + G_B */
+int qfe_expectation_class_part(qfe_ctx* ctx, const qfe_plan* p, int x_hi, const void* bra, const void* ket, int dtype, int part, int n_parts, double* out);
 /* whole-vector convenience (n_local == n): <psi|H|psi> in out[0..1]                            */
 int qfe_expectation(qfe_ctx* ctx, const qfe_plan* p, const void* psi, int dtype, double out[2]);
 /* same through HOST memory: psi_host is uploaded in chunks inside the call (end-to-end path)   */

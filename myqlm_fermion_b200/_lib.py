@@ -50,6 +50,7 @@ SIGNATURES = {
     "qfe_plan_classes": (C.c_int, [C.c_void_p, c_i32_p, C.c_int32]),
     "qfe_plan_destroy": (C.c_int, [C.c_void_p]),
     "qfe_expectation_class": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, c_double_p]),
+    "qfe_expectation_class_part": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, c_double_p]),
     "qfe_expectation": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, c_double_p]),
     "qfe_expectation_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, c_double_p]),
     "qfe_apply_class": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),

@@ -966,8 +966,10 @@ static void fill_sweep_args(const qfe_plan* p, const SweepHost& s, int dtype, Sw
 
 // Runs every sweep of one class in EXPECT or BATCH mode and leaves per-range values in host_vals
 // (EXPECT: one value per sweep; BATCH: one per group, sweep order).
-static int run_class_reduce(qfe_ctx* ctx, const qfe_plan* p, int ci, const void* bra, const void* ket, int dtype, std::vector<double>& host_vals,
-                            std::vector<int32_t>& val_slot) {
+// part / n_parts: only the sweeps si with (si - first sweep of the class) % n_parts == part run (the direct kernel, which has no
+// sweeps, runs in part 0 only): the parts of a class add up to the whole class.
+static int run_class_reduce(qfe_ctx* ctx, const qfe_plan* p, int ci, const void* bra, const void* ket, int dtype, int part, int n_parts,
+                            std::vector<double>& host_vals, std::vector<int32_t>& val_slot) {
     const ClassHost& cls = p->h.classes[ci];
     const bool batch = p->batch;
     const bool tiles = p->h.use_tiles && !p->force_direct;
@@ -975,10 +977,12 @@ static int run_class_reduce(qfe_ctx* ctx, const qfe_plan* p, int ci, const void*
     host_vals.clear();
     val_slot.clear();
     int64_t n_vals = 0;
+    auto mine = [&](int si) { return (si - cls.sweep_begin) % n_parts == part; };
     if (tiles) {
-        for (int si = cls.sweep_begin; si < cls.sweep_end; ++si) n_vals += batch ? (p->h.sweeps[si].group_end - p->h.sweeps[si].group_begin) : 1;
+        for (int si = cls.sweep_begin; si < cls.sweep_end; ++si)
+            if (mine(si)) n_vals += batch ? (p->h.sweeps[si].group_end - p->h.sweeps[si].group_begin) : 1;
     } else {
-        n_vals = batch ? (cls.dgroup_end - cls.dgroup_begin) : 1;
+        n_vals = part != 0 ? 0 : (batch ? (cls.dgroup_end - cls.dgroup_begin) : 1);
     }
     if (n_vals == 0) return QFE_OK;
     QFE_TRY(ctx->result.reserve(sizeof(double2) * n_vals));
@@ -993,6 +997,7 @@ static int run_class_reduce(qfe_ctx* ctx, const qfe_plan* p, int ci, const void*
         }
         QFE_TRY(ctx->partials.reserve(sizeof(double2) * max_partials));
         for (int si = cls.sweep_begin; si < cls.sweep_end; ++si) {
+            if (!mine(si)) continue;
             const SweepHost& sw = p->h.sweeps[si];
             SweepArgs a;
             memset(&a, 0, sizeof(a));
@@ -1169,15 +1174,20 @@ int qfe_plan_destroy(qfe_plan* p) {
 }
 
 int qfe_expectation_class(qfe_ctx* ctx, const qfe_plan* p, int x_hi, const void* bra, const void* ket, int dtype, double* out) {
+    return qfe_expectation_class_part(ctx, p, x_hi, bra, ket, dtype, 0, 1, out);
+}
+
+int qfe_expectation_class_part(qfe_ctx* ctx, const qfe_plan* p, int x_hi, const void* bra, const void* ket, int dtype, int part, int n_parts, double* out) {
     QFE_REQUIRE(ctx && p && bra && ket && out, QFE_ERR_ARG, "qfe_expectation_class: null argument");
     QFE_REQUIRE(dtype == QFE_C128 || dtype == QFE_C64, QFE_ERR_ARG, "unknown dtype %d", dtype);
+    QFE_REQUIRE(n_parts >= 1 && part >= 0 && part < n_parts, QFE_ERR_ARG, "qfe_expectation_class_part: part %d of %d", part, n_parts);
     QFE_CUDA(cudaSetDevice(ctx->device));
     for (int64_t i = 0; i < 2 * p->h.n_slots; ++i) out[i] = 0.0;
     const int ci = find_class(p, x_hi);
     if (ci < 0) return QFE_OK;  // no term flips these high qubits
     std::vector<double> vals;
     std::vector<int32_t> slots;
-    QFE_TRY(run_class_reduce(ctx, p, ci, bra, ket, dtype, vals, slots));
+    QFE_TRY(run_class_reduce(ctx, p, ci, bra, ket, dtype, part, n_parts, vals, slots));
     for (size_t i = 0; i < slots.size(); ++i) {
         out[2 * slots[i]] += vals[2 * i];
         out[2 * slots[i] + 1] += vals[2 * i + 1];

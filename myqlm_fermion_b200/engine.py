@@ -265,9 +265,9 @@ class Engine:
         return out
 
     # ---- shard-level entry points (one x_hi class at a time; ShardedEngine drives these) ------
-    def expectation_class(self, plan: Plan, x_hi: int, bra_shard, ket_shard):
+    def expectation_class(self, plan: Plan, x_hi: int, bra_shard, ket_shard, part: int = 0, n_parts: int = 1):
         """Class x_hi's share of <bra|H|ket>: ``bra_shard`` is this rank's shard of the bra,
-        ``ket_shard`` the shard (shard ^ x_hi) of the ket."""
+        ``ket_shard`` the shard (shard ^ x_hi) of the ket.  ``part`` / ``n_parts``: every n_parts-th sweep of the class only."""
         n_amps = 1 << plan.n_local
         dt = self._check_state(ket_shard, n_amps)
         if self._check_state(bra_shard, n_amps) != dt:
@@ -275,8 +275,8 @@ class Engine:
         self._sync_torch()
         out = np.zeros(2 * plan.terms.n_slots, dtype=np.float64)
         check(
-            self.lib.qfe_expectation_class(
-                self.ctx, plan.handle, x_hi, C.c_void_p(bra_shard.data_ptr()), C.c_void_p(ket_shard.data_ptr()), dt, as_ptr(out, C.c_double)
+            self.lib.qfe_expectation_class_part(
+                self.ctx, plan.handle, x_hi, C.c_void_p(bra_shard.data_ptr()), C.c_void_p(ket_shard.data_ptr()), dt, part, n_parts, as_ptr(out, C.c_double)
             )
         )
         vals = out.view(np.complex128)

@@ -84,28 +84,6 @@ class ShardedEngine:
         self.exchanged_bytes += shard.numel() * shard.element_size()
         return buf
 
-    def exchange_one_way(self, shard, x_hi: int, receive: bool):
-        """Half of ``exchange``: the rank with ``receive`` gets the partner's shard, the other one only sends."""
-        dist = _dist()
-        import torch
-
-        peer = self.rank ^ x_hi
-        peer_global = dist.get_global_rank(self.group, peer) if self.group is not None else peer
-        if receive:
-            buf = self._partner_buffer(shard)
-            ops = [dist.P2POp(dist.irecv, torch.view_as_real(buf), peer_global, group=self.group)]
-        else:
-            buf = None
-            ops = [dist.P2POp(dist.isend, torch.view_as_real(shard), peer_global, group=self.group)]
-        for req in dist.batch_isend_irecv(ops):
-            req.wait()
-        if shard.is_cuda:
-            torch.cuda.current_stream(shard.device).synchronize()
-        if receive:
-            self.exchanges += 1
-            self.exchanged_bytes += shard.numel() * shard.element_size()
-        return buf
-
     def allreduce(self, values: np.ndarray) -> np.ndarray:
         import torch
 
@@ -121,20 +99,16 @@ class ShardedEngine:
         bra = ket_shard if bra_shard is None else bra_shard
         n_slots = plan.terms.n_slots
         acc = np.zeros(n_slots, dtype=np.complex128)
-        # <psi|H|psi> with every class Hermitian: the shard pairs (r, r^x_hi) and (r^x_hi, r) of a class give conjugate numbers, so one
-        # rank of each pair receives its partner's shard and counts the pair twice; the other one only sends.  Workers alternate from
-        # class to class (per pivot bit) so that every rank works on about half of the non-local classes.
-        pair_once = bra_shard is None and n_slots == 1 and getattr(plan, "hermitian", False)
-        seen_pivot = {}
+        # <psi|H|psi> with every class Hermitian: the shard pairs (r, r^x_hi) and (r^x_hi, r) of a class give conjugate numbers.  The
+        # two ranks of a pair split the sweeps of the class between them (each with its own shard as the bra) and count their half
+        # twice: every rank does half of the work of every non-local class.
+        split = bra_shard is None and n_slots == 1 and getattr(plan, "hermitian", False)
         for x_hi in plan.classes:  # the class list is the same on every rank (it depends on the X masks only)
-            if x_hi != 0 and pair_once:
+            if x_hi != 0 and split:
                 pivot = (x_hi & -x_hi).bit_length() - 1
-                pol = seen_pivot.get(pivot, 0)
-                seen_pivot[pivot] = pol ^ 1
-                worker = ((self.rank >> pivot) & 1) == pol
-                partner = self.exchange_one_way(ket_shard, x_hi, receive=worker)
-                if worker:
-                    acc += 2.0 * np.real(np.atleast_1d(self.backend.expectation_class(plan, x_hi, bra, partner)))
+                partner = self.exchange(ket_shard, x_hi)
+                half = self.backend.expectation_class(plan, x_hi, bra, partner, part=(self.rank >> pivot) & 1, n_parts=2)
+                acc += 2.0 * np.real(np.atleast_1d(half))
                 continue
             partner = self.exchange(ket_shard, x_hi)
             acc += np.atleast_1d(self.backend.expectation_class(plan, x_hi, bra, partner))

@@ -66,7 +66,10 @@ class CpuBackend:
         assert rc == 0, rc
         return out, y
 
-    def expectation_class(self, plan, x_hi, bra_shard, ket_shard):
+    def expectation_class(self, plan, x_hi, bra_shard, ket_shard, part=0, n_parts=1):
+        # the interpreter has no notion of sweep subsets: part 0 carries the whole class, the other parts nothing (they still add up)
+        if part != 0:
+            return 0.0 if plan.terms.n_slots == 1 else np.zeros(plan.terms.n_slots, dtype=np.complex128)
         out, _ = self._run(plan, x_hi, bra_shard, ket_shard)
         return complex(out[0]) if plan.terms.n_slots == 1 else out
 
