@@ -270,43 +270,6 @@ int build_plan(const TermView& t, int n_local, int shard, const PlanLimits& lim,
                     }
                     Xs |= uint64_t(1) << best;
                 }
-                // local search on the greedy choice: swap one X position for a free one while that covers more pending groups
-                // (weighted by their work).  Fewer, fuller sweeps: every sweep streams the whole shard through shared memory once.
-                if (popc64(Xs) == xcap && n_local > k) {
-                    auto covered = [&](uint64_t cand) {
-                        double w = 0.0;
-                        for (size_t g = 0; g < ng; ++g)
-                            if (!done[g] && !((need[g] ^ seed) & ~cand)) w += 48.0 + 6.0 * groups[g].nt;
-                        return w;
-                    };
-                    double cur = covered(Xs);
-                    for (int round = 0; round < 12; ++round) {
-                        uint64_t best_set = Xs;
-                        double best_w = cur;
-                        for (uint64_t out_m = Xs; out_m; out_m &= out_m - 1) {
-                            const uint64_t without = Xs & ~(out_m & (~out_m + 1));
-                            // candidates: positions that appear in a pending group missing exactly one bit of `without` + that bit
-                            uint64_t cand_in = 0;
-                            for (size_t g = 0; g < ng; ++g) {
-                                if (done[g]) continue;
-                                const uint64_t miss = (need[g] ^ seed) & ~without;
-                                if (popc64(miss) == 1) cand_in |= miss;
-                            }
-                            cand_in &= ~Xs;
-                            for (uint64_t in_m = cand_in; in_m; in_m &= in_m - 1) {
-                                const uint64_t trial = without | (in_m & (~in_m + 1));
-                                const double w = covered(trial);
-                                if (w > best_w) {
-                                    best_w = w;
-                                    best_set = trial;
-                                }
-                            }
-                        }
-                        if (best_set == Xs) break;
-                        Xs = best_set;
-                        cur = best_w;
-                    }
-                }
                 // register positions: the low bits the X positions left out, then the free positions on which the fewest of the
                 // groups this sweep will take carry Z bits (no Z bit on the register rows = one weight for the 16 rows)
                 uint64_t Rm = lowmask & ~Xs;
