@@ -268,8 +268,11 @@ def main():
     sweep_launches = sweeps_per_step * args.steps
     avg_launch_s = sec / max(sweep_launches, 1)  # upper bound: includes the (tiny) reduce kernels and, for N>1, the exchanges
     achieved = shard_bytes / avg_launch_s / 1e9
+    # DRAM bytes of one sweep launch from the ncu --set full capture under profiles/ (dram__bytes_read.sum + dram__bytes_write.sum;
+    # r01_sweep_v6_32q_ncu.txt: 68.742878 GB + 8.92 MB for a 2^32-amplitude complex128 shard); None where no capture exists
+    ncu_traffic = {(32, "c128"): 68.742878e9 + 8.920320e6}.get((n_local, args.dtype))
     roofline = {
-        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic,
         "kernel": "tile_sweep_kernel<EXPECT>", "peak_source": peak_src, "bytes_per_launch": shard_bytes, "avg_launch_ms": 1e3 * avg_launch_s,
         "terms_per_sweep": T / max(sweeps_per_step, 1),
         "note": "each sweep evaluates terms_per_sweep Pauli terms per amplitude from one HBM pass, so the kernel is issue/shared-memory bound by design; "
