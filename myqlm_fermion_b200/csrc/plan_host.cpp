@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 
@@ -308,10 +309,15 @@ int build_plan(const TermView& t, int n_local, int shard, const PlanLimits& lim,
                 // position waits for a sweep whose X positions hold all its bits (first pass); wide ones have no such sweep.
                 std::vector<size_t> take;
                 int64_t nterms = 0;
-                for (int pass = 0; pass < 2 && take.empty(); ++pass)
+                // A sweep that stays small streams the whole shard for little work: it then also takes the pending groups whose X mask
+                // touches its register positions (slower per group, but one pass over the shard less later on).
+                const char* fill_env = getenv("QFE_PLAN_FILL");  // development knob: 0 disables the fill
+                const int fill_below = fill_env ? atoi(fill_env) : lim.fill_below;
+                for (int pass = 0; pass < 2 && (take.empty() || (pass == 1 && (int)take.size() < fill_below)); ++pass)
                     for (size_t g = 0; g < ng; ++g) {
                         if (done[g] || ((need[g] & ~L) != kxor)) continue;
-                        if (pass == 0 && (need[g] & Rm) && popc64(need[g]) <= xcap) continue;
+                        const bool touches_rows = (need[g] & Rm) && popc64(need[g]) <= xcap;
+                        if (pass == 0 ? touches_rows : (!touches_rows && !take.empty())) continue;  // pass 1 adds what pass 0 deferred
                         const int nt_padded = (groups[g].nt + 1) & ~1;  // staged term lists are padded to an even length
                         if ((int)take.size() >= lim.max_groups || nterms + nt_padded > lim.max_terms) break;
                         take.push_back(g);

@@ -76,6 +76,7 @@ struct SweepArgs {
     const uint32_t* nat_loc;
     int k, n_runs;
     int same_tile, accumulate;
+    int prefetch_dist;  // tiles ahead that go to L2 while the current one is processed (0: off)
     unsigned long long n_tiles;
     unsigned long long ket_xor;
     uint8_t run_pos[PLAN_MAX_RUNS];
@@ -670,9 +671,9 @@ __global__ void __launch_bounds__(NTH, NT_MAX / NTH) tile_sweep_kernel(const __g
         }
         __syncthreads();
         // next tile of this CTA -> L2 while this one is processed (two 128 B lines per thread)
-        if (tile_id + gridDim.x < a.n_tiles) {
+        if (a.prefetch_dist > 0 && tile_id + (unsigned long long)a.prefetch_dist * gridDim.x < a.n_tiles) {
             uint64_t nbase = 0;
-            unsigned long long rest = tile_id + gridDim.x;
+            unsigned long long rest = tile_id + (unsigned long long)a.prefetch_dist * gridDim.x;
             for (int r = 0; r < a.n_runs; ++r) {
                 const int len = a.run_len[r];
                 nbase |= (rest & ((1ull << len) - 1ull)) << a.run_pos[r];
@@ -934,6 +935,10 @@ static void fill_sweep_args(const qfe_plan* p, const SweepHost& s, int dtype, Sw
     a.n_groups = s.group_end - s.group_begin;
     a.n_terms = (int)(s.term_end - s.term_begin);
     a.k = s.k;
+    {
+        const char* pd = getenv("QFE_PREFETCH_DIST");  // development knob
+        a.prefetch_dist = pd ? atoi(pd) : 1;
+    }
     a.n_runs = s.n_runs;
     a.n_tiles = (unsigned long long)s.n_tiles;
     a.ket_xor = s.ket_xor;
