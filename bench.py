@@ -295,8 +295,31 @@ def main():
 
     # ---- e2e: the same step through the C-ABI call with HOST buffers (pinned), H2D inside the timed region ----
     e2e = None
+    e2e_skip = None
     if not args.no_e2e:
-        host = torch.empty(1 << n_local, dtype=tdtype, pin_memory=True)
+        # every rank stages its shard in host memory: make sure the box has room for all of them before pinning
+        try:
+            import psutil
+
+            avail = psutil.virtual_memory().available
+        except Exception:
+            avail = None
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+        ok = not (avail is not None and avail < 1.15 * shard_bytes * local_world)
+        if world > 1:  # one decision for all ranks: the end-to-end leg contains collectives
+            flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            ok = bool(flag.item())
+        if not ok:
+            avail = avail or 0
+            e2e_skip = f"host memory: {avail / 2**30:.0f} GiB available, {shard_bytes * local_world / 2**30:.0f} GiB needed for the shards of {local_world} ranks"
+    if not args.no_e2e and e2e_skip is None:
+        pinned = True
+        try:
+            host = torch.empty(1 << n_local, dtype=tdtype, pin_memory=True)
+        except RuntimeError:
+            host = torch.empty(1 << n_local, dtype=tdtype)
+            pinned = False
         host.copy_(psi)
         torch.cuda.synchronize()
         host_np = host.numpy()
@@ -314,6 +337,7 @@ def main():
         e2e = {
             "value": T * amps * e2e_steps / (ms2 / 1e3), "unit": UNIT, "h2d_bytes_per_step": shard_bytes * world, "d2h_bytes_per_step": 16 * world,
             "steps": e2e_steps, "ms_per_step": ms2 / e2e_steps, "energy_matches_device": bool(abs(energy2 - energy) <= 1e-10 * abs(energy)),
+            "host_memory": "pinned" if pinned else "pageable",
         }
 
     if rank != 0:
@@ -336,8 +360,10 @@ def main():
         "energy": energy.real, "energy_imag": energy.imag, "term_expansion_s": t_terms,
         "hbm_gbs_algorithmic": roofline["achieved"] * world,
     }
+    if e2e_skip is not None:
+        line["e2e_skipped"] = e2e_skip
     if se is not None:
-        line["exchanges_per_step"] = se.exchanges // max(args.warmup + args.steps + (0 if args.no_e2e else 1 + e2e["steps"]), 1)
+        line["exchanges_per_step"] = se.exchanges // max(args.warmup + args.steps + (0 if e2e is None else 1 + e2e["steps"]), 1)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
