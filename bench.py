@@ -192,9 +192,18 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
-        dist.init_process_group("nccl", device_id=dev)
+        # rank 0 prints exactly one JSON line: keep NCCL's version banner (written to stdout when the communicator is created) off it
+        sys.stdout.flush()
+        saved_fd, null_fd = os.dup(1), os.open(os.devnull, os.O_WRONLY)
+        os.dup2(null_fd, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
+            os.close(null_fd)
 
     n = args.qubits or qubits_for(world)
     tdtype = torch.complex128 if args.dtype == "c128" else torch.complex64
