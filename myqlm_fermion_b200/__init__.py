@@ -22,6 +22,7 @@ from .packed import PackedTerms, pack_terms, unpack_term
 from . import plugins
 from .io import load_molecule_npz, load_terms_npz, molecule_hamiltonian, save_molecule_npz, save_terms_npz
 from .transforms import (
+    change_encoding,
     get_bk_code,
     get_jw_code,
     get_parity_code,
@@ -38,6 +39,6 @@ __all__ = [
     "make_anderson_model", "make_hubbard_model", "make_tot_density_op", "normal_order_fermionic_term",
     "PackedTerms", "pack_terms", "unpack_term", "plugins",
     "load_molecule_npz", "load_terms_npz", "molecule_hamiltonian", "save_molecule_npz", "save_terms_npz",
-    "get_bk_code", "get_jw_code", "get_parity_code", "make_PCU_sets", "recode_integer",
+    "change_encoding", "get_bk_code", "get_jw_code", "get_parity_code", "make_PCU_sets", "recode_integer",
     "transform_to_bk_basis", "transform_to_jw_basis", "transform_to_parity_basis",
 ]

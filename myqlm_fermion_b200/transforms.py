@@ -134,3 +134,14 @@ def recode_integer(integer: int, code: np.ndarray) -> int:
     for k in range(n):
         out = (out << 1) | int(p[k])
     return out
+
+
+def change_encoding(mat: np.ndarray, code: np.ndarray) -> np.ndarray:
+    """B[C(i), C(j)] = A[i, j] with C = recode_integer(., code): the basis relabelling the reference's own tests use to compare an
+    encoded spin Hamiltonian with the Fock-space matrix (/root/reference/qat/fermion/transforms.py:380-407, a 4^n Python loop
+    there).  Host-side index permutation of a caller-supplied matrix, not part of the device path."""
+    n = code.shape[0]
+    table = np.array([recode_integer(i, code) for i in range(1 << n)], dtype=np.int64)
+    out = np.zeros(mat.shape, mat.dtype)
+    out[np.ix_(table, table)] = mat
+    return out

@@ -171,3 +171,6 @@ def test_facade_transforms_match_reference_criterion(eng):
             a = fn(h).get_matrix()
             b = transforms.change_encoding(a_f, transforms.code_for(n, enc))
             np.testing.assert_almost_equal(np.linalg.norm(a - b), 0, decimal=10)
+            # the facade's own code matrices and change_encoding (transforms.py:260-407) give the same relabelling
+            code = {"jordan-wigner": qfe.get_jw_code, "parity": qfe.get_parity_code, "bravyi-kitaev": qfe.get_bk_code}[enc](n)
+            assert np.array_equal(qfe.change_encoding(a_f, code), b)

@@ -49,3 +49,22 @@ def test_molecule_file_to_ground_energy_and_term_files(golden_dir, tmp_path):
     for a, b in zip(batch.arrays(), again.arrays()):
         assert np.array_equal(a, b)
 
+
+
+def test_change_encoding_matches_the_reference_loop():
+    """transforms.py:380-407 restated as the double loop, against the facade's vectorised permutation."""
+    import itertools
+
+    import myqlm_fermion_b200 as qfe
+
+    n = 4
+    rng = np.random.default_rng(0)
+    mat = rng.standard_normal((1 << n, 1 << n)) + 1j * rng.standard_normal((1 << n, 1 << n))
+    for code in (qfe.get_jw_code(n), qfe.get_parity_code(n), qfe.get_bk_code(n)):
+        table = [qfe.recode_integer(i, code) for i in range(1 << n)]
+        want = np.zeros_like(mat)
+        for i, j in itertools.product(range(1 << n), repeat=2):
+            want[table[i], table[j]] = mat[i, j]
+        assert np.array_equal(qfe.change_encoding(mat, code), want)
+    for enc, fn in (("jordan-wigner", qfe.get_jw_code), ("parity", qfe.get_parity_code), ("bravyi-kitaev", qfe.get_bk_code)):
+        assert np.array_equal(fn(5), transforms.code_for(5, enc)), enc  # the oracle's code matrices (transforms.py:260-346)
