@@ -62,11 +62,6 @@ enum { KIND_FAST = 0,  // no z bit on the register rows: W is the same for the 1
 //                   word 1 = first term (sweep-local) | kind << 16 | polarity << 18 | skip bit << 24
 constexpr int RNG_KIND_SHIFT = 16, RNG_POL_SHIFT = 18, RNG_SKIP_SHIFT = 24;
 
-// shared-memory word (16 B units for complex128) of tile-local index j: row-major planes, one plane per register row, padded to
-// an odd length so that the 8 rows a quarter warp stages land on 8 distinct bank groups
-constexpr uint32_t PLAN_PLANE = 513;
-inline uint32_t tile_word_of(uint32_t j) { return (j & 15u) * PLAN_PLANE + (j >> PLAN_REG_BITS); }
-
 struct PlanLimits {
     int tile_bits = 13;
     int max_terms = 2048;  // per sweep (shared-memory staging capacity)

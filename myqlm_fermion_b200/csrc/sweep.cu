@@ -4,17 +4,16 @@
 // matrix-vector products at the reference's call sites.  The reference materialises a 2^n x 2^n
 // matrix; here every launch ("sweep") streams the shard through shared memory once:
 //
-//   * a CTA stages one *tile* -- 2^k amplitudes whose index differs only in the k bit positions
-//     the sweep's X masks live in -- with coalesced 128-bit loads (128 B contiguous segments);
-//   * every XOR partner psi[b ^ x] of every term group of the sweep is then a shared-memory read
-//     (conflict-free: a warp reads a permutation of 32 consecutive 16 B words);
-//   * signs come from popc parity: the part of z inside the tile is one __popc per (term, thread)
-//     shared by the thread's R register-blocked rows; the part outside the tile is folded into the
-//     coefficient once per tile;
-//   * W_x(b) = sum_t c_t (-1)^{|z_t & b|} costs one 32-bit select (sign bit of the high word) and
-//     one DADD per (term, amplitude);
-//   * the expectation is reduced by warp shuffles, then per block, then by a fixed-order reduce
-//     kernel (bit-reproducible).
+//   * a CTA stages one *tile* -- 2^k amplitudes whose index differs only in the k bit positions of the sweep (k - 4 positions that
+//     hold its X masks, 4 register positions they avoid) -- with coalesced 128-bit loads (128 B contiguous segments);
+//   * a thread keeps the 16 amplitudes that differ on the register positions in registers; every XOR partner psi[b ^ x] of every
+//     term group of the sweep is a shared-memory read at [register + immediate] (conflict-free: a warp reads a permutation of 32
+//     consecutive 16 B words of one plane);
+//   * signs come from popc parity: the part of z inside the tile is one __popc per (term, thread) shared by the thread's 16 rows;
+//     the part outside the tile is a second mask against the tile number (real-coefficient sweeps keep their term records in the
+//     kernel parameter = constant bank, next to the shared-memory pipe) or folded into the staged coefficient per tile;
+//   * W_x(b) = sum_t c_t (-1)^{|z_t & b|} costs one integer multiply-add on the sign bit and one DADD per (term, thread);
+//   * the expectation is reduced by warp shuffles, then per block, then by a fixed-order reduce kernel (bit-reproducible).
 // No tensor cores: this is an XOR-gather with +-1 weights, not a dense contraction.
 #include <algorithm>
 #include <cstdlib>

@@ -12,6 +12,7 @@ observable evaluations are done by libqfe.
                                                                  (adapt_vqe.py:50-62, 181-195)
 * ``SeqOptim.optimize``                                      <->  SeqOptim.optimize (sequential_optimization.py:104-146)
 * ``vqe_energy``                                             <->  VQE.fun (vqe.py:53-59)
+* ``AdaptVQE.run``                                           <->  AdaptVQEPlugin.run (adapt_vqe.py:143-240), state preparation on the device
 * ``qse_matrices``                                           <->  the H / S loops of the QSE helper (chemistry/qse.py:191-214)
 * ``GradientDescentOptimizer``                               <->  GradientDescentOptimizer.optimize (naturalgradient/qfim_plugin.py:96-251)
 """
@@ -259,3 +260,69 @@ class GradientDescentOptimizer:
             self.iterations += 1
         angle_energy = [(angles[i], self.trace[i]) for i in range(len(self.trace))]
         return self.trace[-1], list(cur_params), {"iterations": self.iterations, "energies": angle_energy}
+
+
+class AdaptVQE:
+    """``AdaptVQEPlugin.run`` (/root/reference/qat/plugins/adapt_vqe.py:143-240) on a device state: per iteration the gradients
+    -i<psi|[H, tau_k]|psi> of the whole pool, the operator with the largest one appended to the ansatz as exp(-i theta tau) term by
+    term (``_grow_ansatz``, :64-141), all angles re-optimised by ``minimizer`` (the role of the optimizer plugin stacked under the
+    reference's plugin; default scipy COBYLA, the reference's test setting), until the gradient norm falls below
+    ``tol_vanishing_grad`` or ``n_iterations`` is reached.  ``Result.meta_data`` holds the reference's four string fields."""
+
+    def __init__(self, operator_pool: Sequence[SpinHamiltonian], n_iterations: int = 300, tol_vanishing_grad: float = 1e-3, minimizer: Optional[Callable] = None,
+                 engine=None):
+        from .engine import get_engine
+
+        self.engine = engine or get_engine()
+        self.pool = list(operator_pool)
+        self.n_iterations = n_iterations
+        self.gradients = AdaptVQEGradients(self.pool, tol_vanishing_grad=tol_vanishing_grad, engine=self.engine)
+        self.minimizer = minimizer or self._cobyla
+
+    @staticmethod
+    def _cobyla(fun, x0):
+        import scipy.optimize
+
+        trace = []
+
+        def wrapped(x):
+            v = fun(x)
+            trace.append(v)
+            return v
+
+        res = scipy.optimize.minimize(wrapped, x0, method="COBYLA", tol=1e-6, options={"maxiter": 500})
+        return float(res.fun), np.atleast_1d(res.x), trace
+
+    def run(self, observable: SpinHamiltonian, initial_basis_state: int) -> Result:
+        eng = self.engine
+        n = observable.nbqbits
+        plan = eng.plan(observable.packed(eng))
+        operator_idx: List[int] = []
+        thetas = np.zeros(0)
+        energy_trace, optimization_trace, n_iters_optim = [], [], []
+
+        def state(params):
+            psi = eng.basis_state(n, initial_basis_state)
+            eng.evolve_operators(psi, [self.pool[k] for k in operator_idx], params)
+            return psi
+
+        def energy(params):
+            return eng.energy(plan, state(params))
+
+        value = energy(thetas)
+        for _ in range(self.n_iterations):
+            grads = self.gradients.gradients(observable, state(thetas))
+            op_ind, _ = self.gradients.select(grads)
+            if op_ind is None:
+                break
+            operator_idx.append(op_ind)
+            value, thetas, trace = self.minimizer(energy, np.append(thetas, 0.0))
+            energy_trace.append(value)
+            n_iters_optim.append(len(trace))
+            optimization_trace += list(trace)
+        res = Result(value=value, parameter_map={f"theta_{i}": float(t) for i, t in enumerate(thetas)})
+        res.meta_data = {
+            "operator_order": str(operator_idx), "energy_trace": str(energy_trace), "optimization_trace": str(optimization_trace),
+            "n_iters_optim": str(n_iters_optim),
+        }
+        return res

@@ -70,7 +70,7 @@ def test_unsharded_plan_reproduces_apply_and_expectation(emul, enc, tile_bits):
     out, y, stats = _run(emul, n, x, z, c, np.zeros(len(x)), 1, [k], n, 0, tile_bits, 0, bra, psi)
     assert np.max(np.abs(y - want_phi)) <= 1e-12 * np.max(np.abs(want_phi))
     assert abs(out[0] - np.vdot(bra, want_phi)) <= 1e-12
-    # <psi|H|psi> with the half-visit of Hermitian groups (what the EXPECT_SAME kernel does)
+    # <psi|H|psi> with the half-visit of Hermitian groups (what the EXPECT kernel does when the bra tile is the ket tile)
     out2, _, _ = _run(emul, n, x, z, c, np.zeros(len(x)), 1, [k], n, 0, tile_bits, 0, psi, psi, half_visit=1)
     want_e = np.vdot(psi, want_phi)
     assert abs(out2[0] - want_e.real) <= 1e-12 * abs(want_e) and abs(want_e.imag) <= 1e-12
