@@ -147,3 +147,63 @@ def test_uccsd_pool_batch(emul):
         want = np.vdot(bra, spin.apply_packed(n, p[0], p[1], p[2], 0.0, psi))
         assert abs(out[i] - want) <= 1e-12, i
     assert stats[1] == K
+
+
+def test_random_plans_property(emul):
+    """Property test over random Pauli sums (hypothesis): any term set, shard geometry, tile size and staging capacity gives a plan
+    whose interpretation equals the oracle's matrix-free formula -- wide masks, X bits on register positions, runs of register-row
+    Z bits, complex coefficients, several operator slots and the Hermitian half visit included."""
+    from hypothesis import HealthCheck, given, settings
+    from hypothesis import strategies as st
+
+    @settings(max_examples=40, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+    @given(
+        n=st.integers(9, 11), tile_bits=st.integers(9, 11), T=st.integers(1, 60), seed=st.integers(0, 10**6), hermitian=st.booleans(),
+        sparse_x=st.booleans(), n_slots=st.integers(1, 3), g=st.integers(0, 2), max_terms=st.sampled_from([16, 64, 2048]),
+    )
+    def run(n, tile_bits, T, seed, hermitian, sparse_x, n_slots, g, max_terms):
+        rng = np.random.default_rng(seed)
+        x = rng.integers(0, 1 << n, size=T, dtype=np.uint64)
+        if sparse_x:  # molecular-like masks: a few X bits, many terms per mask
+            x &= rng.integers(0, 1 << n, size=T, dtype=np.uint64) & rng.integers(0, 1 << n, size=T, dtype=np.uint64)
+            x[: T // 2] = x[0]
+        z = rng.integers(0, 1 << n, size=T, dtype=np.uint64)
+        c = rng.standard_normal(T) + (0 if hermitian else 1j * rng.standard_normal(T))
+        owner = np.sort(rng.integers(0, n_slots, size=T)).astype(np.int32)
+        recs = sorted({(int(o), int(a), int(b)) for o, a, b in zip(owner, x, z) if (a, b) != (0, 0)})
+        if not recs:
+            return
+        owner = np.array([r[0] for r in recs], dtype=np.int32)
+        x = np.array([r[1] for r in recs], dtype=np.uint64)
+        z = np.array([r[2] for r in recs], dtype=np.uint64)
+        c = np.asarray(c[: len(recs)], dtype=np.complex128)
+        consts = rng.standard_normal(n_slots) * (rng.random(n_slots) < 0.5)
+        n_local = n - g
+        tb = min(tile_bits, n_local)
+        if tb < 9:
+            return
+        psi, bra = _state(n, seed % 97), _state(n, seed % 89 + 100)
+        same = hermitian and n_slots == 1
+        if same:
+            bra = psi
+        total = np.zeros(n_slots, dtype=np.complex128)
+        phi = np.zeros(1 << n, dtype=np.complex128)
+        for r in range(1 << g):
+            for x_hi in range(1 << g):
+                own_b = bra[r << n_local : (r + 1) << n_local]
+                own_k = psi[r << n_local : (r + 1) << n_local]
+                partner = psi[(r ^ x_hi) << n_local : ((r ^ x_hi) + 1) << n_local]
+                half = 1 if (same and x_hi == 0) else 0
+                out, y, _ = _run(emul, n, x, z, c, owner, n_slots, consts, n_local, r, tb, x_hi, own_k if half else own_b, partner, max_terms=max_terms,
+                                 max_groups=16 if max_terms == 16 else 512, half_visit=half)
+                total += out
+                phi[r << n_local : (r + 1) << n_local] += y
+        want_phi = np.zeros(1 << n, dtype=np.complex128)
+        for s in range(n_slots):
+            sel = owner == s
+            ph = spin.apply_packed(n, x[sel], z[sel], c[sel], consts[s], psi)
+            assert abs(total[s] - np.vdot(bra, ph)) <= 1e-10, (s, total[s], np.vdot(bra, ph))
+            want_phi += ph
+        assert np.max(np.abs(phi - want_phi)) <= 1e-10
+
+    run()
