@@ -1,0 +1,233 @@
+"""The Hamiltonian objects of the facade against the behaviour the reference's own unit tests pin
+(/root/reference/tests/unitary/test_unitary_hamiltonians.py, test_unitary_transforms.py, test_unitary_trotterization.py):
+same constructors, arithmetic, conversions, exception types, and -- on the GPU -- the same matrices, which the facade obtains
+from the matrix-free engine instead of kron chains."""
+
+import numpy as np
+import pytest
+
+import myqlm_fermion_b200 as qfe
+from myqlm_fermion_b200 import ElectronicStructureHamiltonian, FermionHamiltonian, SpinHamiltonian, Term
+
+
+# ---- host-side object algebra (no GPU) -----------------------------------------------------------------------------------------
+def _h1():
+    return FermionHamiltonian(2, terms=[Term(1.0 + 2j, "CCcc", [1, 0, 1, 0])])
+
+
+def test_adding_and_subtracting_constants():
+    """test_unitary_hamiltonians.py:104-146: a number lands in constant_coeff, on either side."""
+    assert _h1().constant_coeff == 0
+    assert (_h1() + 2).constant_coeff == 2.0
+    assert (2 + _h1()).constant_coeff == 2.0
+    assert (_h1() - 2).constant_coeff == -2.0
+    h = 2 - _h1()
+    assert h.constant_coeff == 2.0
+    t = h.terms[0]
+    assert (t.coeff, t.op, t.qbits) == ((-1 - 2j), "CCcc", [0, 1, 0, 1])
+
+
+def test_adding_subtracting_and_scaling_fermionic_hamiltonians():
+    """:120-127, :149-187: terms are normal ordered (CCcc on ascending creation / annihilation indices, sign from the swaps) and merged."""
+    h2 = FermionHamiltonian(2, terms=[Term(1.0, "CCcc", [0, 1, 1, 0])])
+    t = (_h1() + h2).terms[0]
+    assert (t.coeff, t.op, t.qbits) == (2j, "CCcc", [0, 1, 0, 1])
+    t = (_h1() - h2).terms[0]
+    assert (t.coeff, t.op, t.qbits) == ((2 + 2j), "CCcc", [0, 1, 0, 1])
+    for h in (2 * _h1(), _h1() * 2):
+        t = h.terms[0]
+        assert (t.coeff, t.op, t.qbits) == ((2 + 4j), "CCcc", [0, 1, 0, 1])
+    h = _h1() * h2  # (n_0 n_1)^2 = n_0 n_1
+    t = h.terms[0]
+    assert (t.coeff, t.op, t.qbits, h.constant_coeff) == ((1 + 2j), "CCcc", [0, 1, 0, 1], 0.0)
+
+
+def test_to_electronic_collects_normal_ordered_terms():
+    """:61-73: c+_0 c_0 + (c+_0 c_1 c+_1 c_0 = n_0 - n_0 n_1) -> hpq[0,0] = 2, hpqrs term on [0, 1, 0, 1] with coefficient 1."""
+    h = FermionHamiltonian(2, terms=[Term(1, "Cc", [0, 0]), Term(1, "CcCc", [0, 1, 1, 0])])
+    h_elec = h.to_electronic()
+    assert isinstance(h_elec, ElectronicStructureHamiltonian) and len(h.terms) == 2
+    seen = set()
+    for t in h_elec.terms:
+        if t.op == "Cc":
+            assert t.coeff == 2 and t.qbits == [0, 0]
+        if t.op == "CCcc":
+            assert t.coeff == 1 and t.qbits == [0, 1, 0, 1]
+        seen.add(t.op)
+    assert seen == {"Cc", "CCcc"}
+
+
+def test_operator_letters_are_checked():
+    """:76-85: a fermionic letter in a spin Hamiltonian and a Pauli letter in a fermionic one raise TypeError."""
+    with pytest.raises(TypeError):
+        SpinHamiltonian(2, terms=[Term(1.0, "Cc", [0, 1])])
+    with pytest.raises(TypeError):
+        FermionHamiltonian(2, terms=[Term(1.0, "XY", [0, 1])])
+
+
+def test_unknown_transformation_is_a_key_error():
+    """hamiltonians.py:454: to_spin looks the method up in a dict."""
+    with pytest.raises(KeyError):
+        FermionHamiltonian(2, [Term(0.3, "Cc", [0, 1])]).to_spin("not-a-transform")
+
+
+# ---- matrices (GPU: the facade computes them with the matrix-free engine) -------------------------------------------------------------
+def _spin_example():
+    return SpinHamiltonian(2, [Term(0.5, "X", [0]), Term(0.25, "Y", [1]), Term(1.0, "ZZ", [0, 1])], 0.0)
+
+
+_SPIN_MATRIX = np.array(
+    [[1.0, -0.25j, 0.5, 0.0], [0.25j, -1.0, 0.0, 0.5], [0.5, 0.0, -1.0, -0.25j], [0.0, 0.5, 0.25j, 1.0]], dtype=np.complex128
+)
+_FERMI_MATRIX = np.zeros((4, 4), dtype=np.complex128)
+_FERMI_MATRIX[2, 1] = 1.0
+_FERMI_MATRIX[3, 3] = -0.5
+
+
+@pytest.mark.gpu
+def test_spin_matrix_golden_and_lowest_eigenvalue():
+    """:14-34 and :252-276: the 4x4 golden matrix, dense and sparse, and min eigenvalue -1.25 to 13 decimals."""
+    h = _spin_example()
+    np.testing.assert_equal(h.get_matrix(), _SPIN_MATRIX)
+    np.testing.assert_equal(h.get_matrix(sparse=True).toarray(), _SPIN_MATRIX)
+    np.testing.assert_almost_equal(min(np.linalg.eigh(h.get_matrix())[0]), -1.25, decimal=13)
+
+
+@pytest.mark.gpu
+def test_fermionic_and_electronic_matrix_goldens():
+    """:279-311: Fock-space matrix of c+_0 c_1 + 0.5 c+_0 c+_1 c_0 c_1, unchanged by to_electronic; dag() conjugates."""
+    h = FermionHamiltonian(2, [Term(1.0, "Cc", [0, 1]), Term(0.5, "CCcc", [0, 1, 0, 1])])
+    for obj in (h, h.to_electronic()):
+        np.testing.assert_equal(obj.get_matrix(), _FERMI_MATRIX)
+        np.testing.assert_equal(obj.get_matrix(sparse=True).toarray(), _FERMI_MATRIX)
+    hj = FermionHamiltonian(2, [Term(1.0j, "Cc", [0, 1]), Term(0.5j, "CCcc", [0, 1, 0, 1])]).to_electronic()
+    np.testing.assert_equal(np.conj(hj.get_matrix()), hj.dag().get_matrix())
+
+
+@pytest.mark.gpu
+def test_to_spin_and_to_electronic_keep_the_matrix_and_spectrum():
+    """:37-58, :88-101."""
+    h = FermionHamiltonian(2, [Term(0.3, "Cc", [0, 1]), Term(1.4, "CcCc", [0, 1, 1, 0])])
+    spin_h = h.to_spin()
+    assert all("C" not in t.op and "c" not in t.op for t in spin_h.terms)
+    np.testing.assert_equal(h.get_matrix(), spin_h.get_matrix())
+    compatible = FermionHamiltonian(2, [Term(0.3, "Cc", [0, 1]), Term(1.4, "CCcc", [0, 1, 1, 0])])
+    np.testing.assert_equal(compatible.get_matrix(), compatible.to_electronic().get_matrix())
+    h3 = FermionHamiltonian(3, [Term(1.0, "Cc", [0, 1]), Term(0.5, "CCcc", [0, 1, 0, 1])])
+    spectra = [sorted(np.linalg.eigvals(o.get_matrix())) for o in (h3, h3.to_spin(), h3.to_electronic())]
+    np.testing.assert_equal(spectra[0], spectra[1])
+    np.testing.assert_equal(spectra[0], spectra[2])
+
+
+@pytest.mark.gpu
+def test_matrices_follow_changed_terms_integrals_and_constants():
+    """:190-248: set_terms, the hpqrs setter and constant_coeff are picked up by the next get_matrix."""
+    s = _spin_example()
+    m1 = s.get_matrix()
+    s.set_terms([Term(0.5, "Z", [0]), Term(0.5, "X", [1]), Term(1.0, "XX", [0, 1])])
+    assert not np.all(np.equal(m1, s.get_matrix()))
+    f = FermionHamiltonian(2, [Term(1.0, "Cc", [0, 1]), Term(0.5, "CCcc", [0, 1, 0, 1])])
+    m1 = f.get_matrix()
+    f.set_terms([Term(0.2, "Cc", [0, 1]), Term(2, "CCcc", [0, 1, 1, 0])])
+    assert not np.all(np.equal(m1, f.get_matrix()))
+    e = FermionHamiltonian(2, [Term(1.0, "Cc", [0, 1]), Term(0.5, "CCcc", [0, 1, 0, 1])]).to_electronic()
+    m1 = e.get_matrix()
+    e.hpqrs = np.zeros(e.hpqrs.shape)
+    m2 = e.get_matrix()
+    assert not np.all(np.equal(m1, m2))
+    e.constant_coeff += 3
+    assert np.all(np.equal(e.get_matrix(), m2 + 3 * np.eye(4, 4)))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("transform, code", [(qfe.transform_to_jw_basis, qfe.get_jw_code), (qfe.transform_to_parity_basis, qfe.get_parity_code),
+                                             (qfe.transform_to_bk_basis, qfe.get_bk_code)])
+def test_transforms_match_the_recoded_fock_matrix(transform, code):
+    """test_unitary_transforms.py:23-52: ||T(H).get_matrix() - change_encoding(H.get_matrix(), code)|| = 0 to 10 decimals."""
+    n = 5
+    for terms in ([Term(1.0, "C", [0])], [Term(1.0, "CCcc", [0, 1, 1, 0]), Term(1.0, "CCcc", [1, 0, 0, 1]), Term(0.1, "Cc", [1, 0])]):
+        h = FermionHamiltonian(n, terms, normal_order=False)
+        np.testing.assert_almost_equal(np.linalg.norm(transform(h).get_matrix() - qfe.change_encoding(h.get_matrix(), code(n))), 0, decimal=10)
+
+
+# ---- normal ordering (test_unitary_fermion_algebra.py) -------------------------------------------------------------------------
+def test_normal_ordering_of_single_terms():
+    from myqlm_fermion_b200 import FermionicTerm, normal_order_fermionic_term
+
+    new_terms = normal_order_fermionic_term(FermionicTerm(1, "CcCc", [0, 1, 1, 0]))
+    assert len(new_terms) == 2
+    for t in new_terms:
+        if t.op == "Cc":
+            assert t.qbits == [0, 0] and t.coeff == 1
+        if t.op == "CCcc":
+            assert t.qbits == [0, 1, 0, 1] and t.coeff == 1
+    for letter in "cC":
+        (t,) = normal_order_fermionic_term(FermionicTerm(1.0, letter, [0]))
+        assert (t.op, t.coeff, t.qbits) == (letter, 1.0, [0])
+    for op in ("CC", "cc"):  # one swap: a sign, indices ascending
+        (t,) = normal_order_fermionic_term(FermionicTerm(2.0, op, [1, 0]))
+        assert (t.coeff, t.op, t.qbits) == (-2.0, op, [0, 1])
+
+
+# ---- Trotter slices (test_unitary_trotterization.py) ------------------------------------------------------------------------------
+def _slice_unitary(hs, coeff=1.0):
+    """Columns = the slice applied to every basis state, on the device."""
+    import torch
+
+    eng = qfe.get_engine(0)
+    n = hs.nbqbits
+    cols = []
+    for b in range(1 << n):
+        psi = eng.basis_state(n, b)
+        eng.trotter_slice(hs, psi, coeff=coeff)
+        cols.append(psi)
+    return torch.stack(cols, dim=1).cpu().numpy()
+
+
+def _check_slice_is_the_exponential(hs, decimal=10):
+    import scipy.linalg
+
+    hm = hs.get_matrix() - hs.constant_coeff * np.eye(1 << hs.nbqbits)  # a spin slice has no gate for the identity term
+    np.testing.assert_almost_equal(np.linalg.norm(scipy.linalg.expm(-1j * hm) - _slice_unitary(hs)), 0, decimal=decimal)
+
+
+def _electronic(n, one=(), two=()):
+    hpq = np.zeros((n, n))
+    hpqrs = np.zeros((n, n, n, n))
+    for idx, v in one:
+        hpq[idx] = v
+    for idx, v in two:
+        hpqrs[idx] = v
+    return ElectronicStructureHamiltonian(hpq, hpqrs)
+
+
+@pytest.mark.gpu
+def test_trotter_slices_of_single_fermionic_operators_are_exact():
+    """The operator families of test_unitary_trotterization.py:79-198 (number, excitation, Coulomb / exchange, number-excitation,
+    double excitation): the Jordan-Wigner strings of each commute, so one slice exp(-i c_t P_t) ... is exp(-iH) itself, up to the
+    global phase of the identity term."""
+    cases = [
+        _electronic(2, one=[((1, 1), 2)]),
+        _electronic(2, one=[((0, 1), 2), ((1, 0), 2)]),
+        _electronic(5, one=[((4, 0), 2), ((0, 4), 2)]),
+        _electronic(3, two=[((0, 2, 2, 0), -1.5)]),
+        _electronic(4, two=[((3, 0, 0, 3), 6.5489)]),
+        _electronic(3, two=[((2, 1, 1, 0), -1.5), ((0, 1, 1, 2), -1.5)]),
+        _electronic(5, two=[((4, 0, 0, 1), -1.5), ((1, 0, 0, 4), -1.5)]),
+        _electronic(5, two=[((2, 4, 4, 0), -1.5), ((0, 4, 4, 2), -1.5)]),
+        _electronic(4, two=[((3, 2, 1, 0), -2), ((0, 1, 2, 3), -2)]),
+        _electronic(6, two=[((5, 3, 2, 0), 2.25), ((0, 2, 3, 5), 2.25)]),
+        _electronic(6, two=[((5, 3, 1, 0), 4.587), ((0, 1, 3, 5), 4.587)]),
+    ]
+    for h in cases:
+        _check_slice_is_the_exponential(h.to_spin("jordan-wigner"))
+
+
+@pytest.mark.gpu
+def test_spin_trotter_slices():
+    """:201-260: single ZZ / XX terms exactly; a random sum of ten two-qubit strings with small angles to 3 decimals like the reference."""
+    _check_slice_is_the_exponential(SpinHamiltonian(2, terms=[Term(0.543, "ZZ", [0, 1])]))
+    _check_slice_is_the_exponential(SpinHamiltonian(2, terms=[Term(0.3, "XX", [0, 1])]))
+    rng = np.random.default_rng(0)
+    terms = [Term(0.01 * rng.standard_normal(), "".join(rng.choice(list("XYZ"), 2)), [0, 1]) for _ in range(10)]
+    _check_slice_is_the_exponential(SpinHamiltonian(2, terms=terms), decimal=3)
