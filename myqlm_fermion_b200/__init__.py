@@ -13,7 +13,10 @@ from .hamiltonians import (
     FermionicTerm,
     SpinHamiltonian,
     Term,
+    ind_clusters_ord,
+    ind_spins_ord,
     make_anderson_model,
+    make_embedded_model,
     make_hubbard_model,
     make_tot_density_op,
     normal_order_fermionic_term,
@@ -36,7 +39,7 @@ from .transforms import (
 __all__ = [
     "QfeError", "load_library", "Engine", "Plan", "get_engine",
     "ElectronicStructureHamiltonian", "FermionHamiltonian", "FermionicTerm", "SpinHamiltonian", "Term",
-    "make_anderson_model", "make_hubbard_model", "make_tot_density_op", "normal_order_fermionic_term",
+    "ind_clusters_ord", "ind_spins_ord", "make_anderson_model", "make_embedded_model", "make_hubbard_model", "make_tot_density_op", "normal_order_fermionic_term",
     "PackedTerms", "pack_terms", "unpack_term", "plugins",
     "load_molecule_npz", "load_terms_npz", "molecule_hamiltonian", "save_molecule_npz", "save_terms_npz",
     "change_encoding", "get_bk_code", "get_jw_code", "get_parity_code", "make_PCU_sets", "recode_integer",

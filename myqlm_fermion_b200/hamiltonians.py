@@ -504,5 +504,58 @@ def make_anderson_model(u: float, mu: float, v: np.ndarray, epsilon: np.ndarray)
     return ElectronicStructureHamiltonian(hpq, hpqrs)
 
 
+def ind_clusters_ord(i: int, n_orb: int) -> int:
+    """Cluster-ordered index (up, dn, ..., up, dn) of the spin-orbital with spin-ordered index i (hamiltonians.py:833-855)."""
+    if i < n_orb:
+        return 2 * i
+    if i >= 2 * n_orb:
+        print("index must be lesser than 2*n_orb")
+        return None
+    return 2 * i - (2 * n_orb - 1)
+
+
+def ind_spins_ord(i: int, n_orb: int) -> int:
+    """Spin-ordered index (all up, then all down) of the spin-orbital with cluster-ordered index i (hamiltonians.py:858-871)."""
+    return i // 2 if i % 2 == 0 else (i - 1) // 2 + n_orb
+
+
+def make_embedded_model(u: float, mu: float, D: np.ndarray, lambda_c: np.ndarray, t_loc: Optional[np.ndarray] = None,
+                        int_kernel: Optional[np.ndarray] = None, grouping: Optional[str] = "spins") -> ElectronicStructureHamiltonian:
+    """Impurity cluster (M spin-orbitals) hybridised with an uncorrelated bath cluster (M spin-orbitals), as
+    /root/reference/qat/fermion/hamiltonians.py:732-830 fills it: h_pq = -mu on the impurity levels (+ t_loc), D and D^dagger between
+    the clusters, -lambda_c on the bath (lambda_c f f^dagger = tr(lambda_c) - lambda_c f^dagger f: the trace goes to constant_coeff);
+    h_pqrs = -u * int_kernel, or -u on the (up, down) pairs of the impurity orbitals.  ``grouping="spins"`` reorders h_pq from the
+    cluster order (up, dn, up, dn, ...) to (all up, all down), exactly as the reference does (h_pqrs entries are then placed with
+    ind_clusters_ord)."""
+    M = np.shape(lambda_c)[0]
+    D = np.asarray(D)
+    lambda_c = np.asarray(lambda_c)
+    h_pq = np.zeros((2 * M, 2 * M), dtype=np.complex128)
+    h_pq[:M, :M] = -mu * np.eye(M)
+    if t_loc is not None:
+        h_pq[:M, :M] += np.asarray(t_loc)
+    h_pq[M:, M:] = -lambda_c
+    h_pq[:M, M:] = D
+    h_pq[M:, :M] = np.conj(D).T
+    const_coeff = np.trace(lambda_c)
+    h_pqrs = np.zeros((2 * M, 2 * M, 2 * M, 2 * M)) if int_kernel is None else -u * np.asarray(int_kernel)
+    if grouping == "spins":
+        perm = np.zeros((2 * M, 2 * M))  # from spin order to cluster order
+        perm[2 * np.arange(M), np.arange(M)] = 1
+        perm[2 * np.arange(M) + 1, np.arange(M) + M] = 1
+        if int_kernel is None and u != 0:
+            for i in range(M // 2):
+                a, b = ind_clusters_ord(2 * i, M), ind_clusters_ord(2 * i + 1, M)
+                h_pqrs[a, b, a, b] = h_pqrs[b, a, b, a] = -u
+        h_pq = perm @ h_pq @ perm.T
+    elif grouping == "clusters":
+        if int_kernel is None and u != 0:
+            for i in range(M // 2):
+                h_pqrs[2 * i, 2 * i + 1, 2 * i, 2 * i + 1] = h_pqrs[2 * i + 1, 2 * i, 2 * i + 1, 2 * i] = -u  # sign of the c+ c+ c c form
+    else:
+        print("Grouping must be either clusters or spins.")
+    return ElectronicStructureHamiltonian(h_pq, h_pqrs, const_coeff)
+
+
 def make_tot_density_op(n_sites: int) -> ElectronicStructureHamiltonian:
     return ElectronicStructureHamiltonian(hpq=np.identity(2 * n_sites))

@@ -231,3 +231,61 @@ def test_spin_trotter_slices():
     rng = np.random.default_rng(0)
     terms = [Term(0.01 * rng.standard_normal(), "".join(rng.choice(list("XYZ"), 2)), [0, 1]) for _ in range(10)]
     _check_slice_is_the_exponential(SpinHamiltonian(2, terms=terms), decimal=3)
+
+
+# ---- model generators (tests/integration/test_integration_models.py) ---------------------------------------------------------------
+def test_embedded_model_index_maps_are_inverse():
+    for n_orb in (1, 2, 5):
+        assert [qfe.ind_spins_ord(qfe.ind_clusters_ord(i, n_orb), n_orb) for i in range(2 * n_orb)] == list(range(2 * n_orb))
+        assert sorted(qfe.ind_clusters_ord(i, n_orb) for i in range(2 * n_orb)) == list(range(2 * n_orb))
+
+
+@pytest.mark.gpu
+def test_anderson_model_is_an_embedded_model():
+    """:13-21: one bath level; the embedded model carries tr(lambda_c) in constant_coeff, set to zero as in the reference test."""
+    U = 1
+    mu = U / 2
+    anderson = qfe.make_anderson_model(U, mu, [0.4], [0.04])
+    embedded = qfe.make_embedded_model(U, mu, np.diag([0.4, 0.4]), -0.04 * np.eye(2), grouping="clusters")
+    embedded.constant_coeff = 0
+    diff = np.real(anderson.get_matrix(sparse=True)) - np.real(embedded.get_matrix(sparse=True))
+    assert np.max(np.abs(diff)) < 1e-8
+
+
+@pytest.mark.gpu
+def test_risb_embedding_against_fock_space_operators():
+    """:24-106: two impurity orbitals + bath, random D / lambda_c / t_loc, an explicit interaction kernel; the lowest eigenvalue equals
+    the one of the Hamiltonian assembled from Fock-space creation operators (oracle/fock.py restates util.init_creation_ops)."""
+    import itertools
+
+    from scipy.sparse.linalg import eigsh
+
+    from oracle import fock
+
+    Nc = 2
+    M = 2 * Nc
+    U = 0.1
+    mu = U / 2
+    rng = np.random.RandomState(0)
+    D = np.diag(rng.random_sample(4))
+    lambda_c = np.diag(rng.random_sample(4))
+    t_pm = np.diag(rng.random_sample(4))
+    d_dag = fock.creation_operators(2 * M, sparse=True)
+    d = {i: m.conj().T for i, m in d_dag.items()}
+    ii, jj, kk, ll = np.indices((M, M, M, M))
+    int_kernel = 1.0 * (((ii == jj) & (ii % 2 == 0) & (kk == ll) & (kk == ii + 1)) | ((ii == jj) & (ii % 2 == 1) & (kk == ll) & (kk == ii - 1)))
+    kernel_cccc = 1.0 * (((ii == kk) & (ii % 2 == 0) & (jj == ll) & (jj == ii + 1)) | ((ii == kk) & (ii % 2 == 1) & (jj == ll) & (jj == ii - 1)))
+    extended = np.zeros((2 * M, 2 * M, 2 * M, 2 * M))
+    extended[:M, :M, :M, :M] = kernel_cccc
+    int_term = U / 2 * sum(int_kernel[i, j, k, l] * d_dag[i].dot(d[j]).dot(d_dag[k]).dot(d[l])
+                           for i, j, k, l in itertools.product(range(M), repeat=4) if int_kernel[i, j, k, l])
+    non_int = (
+        sum(lambda_c[i, j] * d[M + j].dot(d_dag[M + i]) for i, j in itertools.product(range(M), repeat=2) if lambda_c[i, j])
+        + sum(D[i, j] * d_dag[i].dot(d[M + j]) + np.conj(D[i, j]) * d_dag[M + j].dot(d[i]) for i, j in itertools.product(range(M), repeat=2) if D[i, j])
+        + sum(t_pm[i, j] * d_dag[i].dot(d[j]) for i, j in itertools.product(range(M), repeat=2) if t_pm[i, j])
+        - mu * sum(d_dag[i].dot(d[i]) for i in range(M))
+    )
+    h_emb = qfe.make_embedded_model(U, mu, D, lambda_c, t_loc=t_pm, int_kernel=extended, grouping="clusters").get_matrix(sparse=True)
+    eig = eigsh(h_emb, k=6, which="SA")[0]
+    want = eigsh(non_int + int_term, k=6, which="SA")[0]
+    np.testing.assert_almost_equal(min(eig), min(want), decimal=7)
