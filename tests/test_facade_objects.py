@@ -289,3 +289,43 @@ def test_risb_embedding_against_fock_space_operators():
     eig = eigsh(h_emb, k=6, which="SA")[0]
     want = eigsh(non_int + int_term, k=6, which="SA")[0]
     np.testing.assert_almost_equal(min(eig), min(want), decimal=7)
+
+
+# ---- H2 through the facade (tests/integration/test_integration_fermionic_algebra.py:13-61) ---------------------------------------------
+def test_cluster_ops_and_hf_ket_match_the_oracle_generators():
+    from oracle import models
+
+    for n_e, n in ((2, 4), (4, 8), (2, 6)):
+        ops = qfe.get_cluster_ops(n_e, nqbits=n)
+        ref = models.cluster_ops(n_e, n)
+        assert len(ops) == len(ref)
+        raw = qfe.workloads.uccsd_pool_fermion_terms(n_e, n)  # what the facade wraps, before FermionHamiltonian normal-orders it
+        assert [[(complex(c), o, list(q)) for c, o, q in t] for t in raw] == [[(complex(c), o, list(q)) for c, o, q in t] for t in ref]
+        for op, terms in zip(ops, ref):
+            assert len(op.terms) == 2 and {t.op for t in op.terms} == {terms[0][1]}
+            assert sorted(abs(t.coeff) for t in op.terms) == [1.0, 1.0] and sum(t.coeff for t in op.terms) == 0  # i(T - T^dagger)
+            assert sorted(sorted(t.qbits) for t in op.terms) == sorted(sorted(q) for _, _, q in terms)
+        assert qfe.get_hf_ket(n_e, n) == models.hf_ket(n_e, n)
+    assert len(qfe.get_cluster_ops(4, noons=[1.9, 1.8, 0.2, 0.1])) == len(qfe.get_cluster_ops(4, nqbits=8))
+    with pytest.raises(TypeError):
+        qfe.get_cluster_ops(2)
+    with pytest.raises(ValueError):
+        qfe.get_cluster_ops(2, nqbits=5)
+    with pytest.raises(ValueError):
+        qfe.get_cluster_ops(3, nqbits=4)
+
+
+@pytest.mark.gpu
+def test_h2_spectra_and_commutators_across_encodings(golden_dir):
+    """H = molecule file -> ElectronicStructureHamiltonian; its spectrum survives to_fermion(); for every UCCSD cluster operator the
+    commutator [H, tau] has the same spectrum in Fock space and in the JW / BK / parity spin encodings."""
+    h, n_e = qfe.molecule_hamiltonian(golden_dir / "h2_integrals.npz")
+    np.testing.assert_almost_equal(sorted(np.linalg.eigvals(h.get_matrix())), sorted(np.linalg.eigvals(h.to_fermion().get_matrix())))
+    h_sp = h.to_spin()
+    for c_op in qfe.get_cluster_ops(n_e, nqbits=h.nbqbits):
+        fermion = np.linalg.eigvals((h | c_op).get_matrix())
+        spins = [(h_sp | c_op.to_spin()).get_matrix()] + [(h.to_spin(enc) | c_op.to_spin(enc)).get_matrix() for enc in ("jordan-wigner", "bravyi-kitaev", "parity")]
+        for m in spins:
+            ev = np.linalg.eigvals(m)
+            np.testing.assert_almost_equal(sorted(np.real(fermion)), sorted(np.real(ev)))
+            np.testing.assert_almost_equal(sorted(np.imag(fermion)), sorted(np.imag(ev)))
