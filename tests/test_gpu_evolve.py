@@ -256,3 +256,69 @@ def test_adapt_vqe_loop_on_h2_reaches_the_exact_energy(eng, golden_dir):
     trace = eval(res.meta_data["energy_trace"])
     assert 1 <= len(order) <= len(pool) and len(trace) == len(order) and all(isinstance(v, str) for v in res.meta_data.values())
     assert all(b <= a + 1e-9 for a, b in zip(trace, trace[1:]))  # the energy never rises when the ansatz grows
+
+
+def _shallow_circuit_on_device(eng, theta):
+    """make_shallow_circ (/root/reference/qat/fermion/circuits.py:207-232) on |0000> with Pauli rotations only:
+    RY(t) = exp(-i t/2 Y);  CNOT(c, t) = e^{-i pi/4} exp(+i pi/4 Z_c) exp(+i pi/4 X_t) exp(-i pi/4 Z_c X_t) (global phase dropped)."""
+    import myqlm_fermion_b200 as qfe
+
+    n = 4
+    gates = []
+
+    def ry(q, t):
+        gates.append((qfe.Term(1.0, "Y", [q]), t / 2))
+
+    def cnot(c, t):
+        gates.extend([(qfe.Term(1.0, "Z", [c]), -np.pi / 4), (qfe.Term(1.0, "X", [t]), -np.pi / 4), (qfe.Term(1.0, "ZX", [c, t]), np.pi / 4)])
+
+    for i in range(4):
+        ry(i, theta[i])
+    cnot(2, 3)
+    ry(2, theta[4])
+    ry(3, theta[5])
+    cnot(0, 2)
+    ry(0, theta[6])
+    ry(2, theta[7])
+    cnot(0, 1)
+    x, z, c = qfe.pack_terms(n, [g for g, _ in gates])
+    assert np.all(c == 1)
+    psi = eng.basis_state(n, 0)
+    eng.pauli_rotations(psi, x, z, [a for _, a in gates])
+    return psi
+
+
+def _embedded_hamiltonian(eng):
+    hpq = np.array([[0.5, 1, 0, 0], [1, 1, 0, 0], [0, 0, 0.5, 1], [0, 0, 1, 1]], dtype=float)
+    hpqrs = np.zeros((4, 4, 4, 4))
+    hpqrs[0, 2, 0, 2] = hpqrs[2, 0, 2, 0] = -1
+    return eng.terms_from_integrals(hpq, hpqrs)
+
+
+def test_golden_energies_with_the_circuit_built_on_the_device(eng, goldens):
+    """The reference's two 12-decimal goldens with every step on the GPU: the ZNE test's energy of the shallow circuit at
+    np.random.seed(0) angles (tests/integration/test_integration_zne_plugin.py:16-49) and the SeqOptim (rotosolve) end energy from
+    seed-1 angles after 10 cycles (tests/integration/test_integration_seqoptim.py:16-33)."""
+    import myqlm_fermion_b200 as qfe
+    from oracle import circuits
+
+    terms = _embedded_hamiltonian(eng)
+    plan = eng.plan(terms)
+    np.random.seed(0)
+    theta = np.random.random(8)
+    psi = _shallow_circuit_on_device(eng, theta)
+    want_psi = circuits.shallow_circuit_state(theta)
+    got_psi = psi.cpu().numpy()
+    phase = np.vdot(want_psi, got_psi)
+    assert abs(abs(phase) - 1) < 1e-12 and np.max(np.abs(got_psi - phase * want_psi)) < 1e-12  # equal up to the dropped global phase
+    g = goldens["scalars"]["zne_energy_shallow_seed0"]
+    np.testing.assert_almost_equal(eng.energy(plan, psi), g["value"], decimal=g["decimals"])
+
+    np.random.seed(1)
+    x0 = np.random.random(8)
+    names = [f"theta_{i}" for i in range(8)]
+    opt = qfe.plugins.SeqOptim(ncycles=10, x0=x0)
+    e, params, _ = opt.optimize(names, lambda p: eng.energy(plan, _shallow_circuit_on_device(eng, [p[k] for k in names])))
+    g = goldens["scalars"]["seqoptim_energy_seed1"]
+    np.testing.assert_almost_equal(e, g["value"], decimal=g["decimals"])
+    assert opt.n_evaluations == 1 + 10 * 8 * 3
