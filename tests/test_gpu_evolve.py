@@ -322,3 +322,51 @@ def test_golden_energies_with_the_circuit_built_on_the_device(eng, goldens):
     g = goldens["scalars"]["seqoptim_energy_seed1"]
     np.testing.assert_almost_equal(e, g["value"], decimal=g["decimals"])
     assert opt.n_evaluations == 1 + 10 * 8 * 3
+
+
+@pytest.mark.parametrize("natural", [False, True])
+def test_gradient_descent_reaches_the_exact_energy_like_the_reference_test(eng, natural):
+    """tests/integration/test_integration_natural_gradient_plugin.py:16-83: one-site Hubbard model (2 qubits), ansatz
+    H(0) RY(t0, 0) CNOT(0, 1) RX(t1, 1), x0 from np.random.seed(1234), maxiter 100, step 0.2, tol 1e-7; the optimised energy equals the
+    exact one to 4 decimals.  State and derivative states are built on the device from Pauli rotations and single-string applies."""
+    import myqlm_fermion_b200 as qfe
+
+    hs = qfe.make_hubbard_model(np.zeros((1, 1)), 2.0, mu=1.0).to_spin()
+    exact = min(np.linalg.eigh(hs.get_matrix())[0])
+    T = qfe.Term
+    pack = lambda terms: qfe.pack_terms(2, terms)[:2]
+    # H = RY(pi/2) Z and CNOT = exp(i pi/4 Z_c) exp(i pi/4 X_t) exp(-i pi/4 Z_c X_t), both up to a global phase
+    pre = [(T(1.0, "Z", [0]), np.pi / 2), (T(1.0, "Y", [0]), np.pi / 4)]
+    cnot = [(T(1.0, "Z", [0]), -np.pi / 4), (T(1.0, "X", [1]), -np.pi / 4), (T(1.0, "ZX", [0, 1]), np.pi / 4)]
+    y0 = eng.terms_from_pauli(2, *pack([T(1.0, "Y", [0])]), [1.0])
+    x1 = eng.terms_from_pauli(2, *pack([T(1.0, "X", [1])]), [1.0])
+
+    def rot(psi, gates):
+        x, z = pack([g for g, _ in gates])
+        eng.pauli_rotations(psi, x, z, [a for _, a in gates])
+
+    def state_and_derivatives(theta):
+        a = eng.basis_state(2, 0)
+        rot(a, pre + [(T(1.0, "Y", [0]), theta[0] / 2)])
+        psi = a.clone()
+        rot(psi, cnot + [(T(1.0, "X", [1]), theta[1] / 2)])
+        d0 = eng.apply(y0, a)  # d/dt0 RY(t0) = -i/2 Y RY(t0)
+        eng.scale(d0, -0.5j)
+        rot(d0, cnot + [(T(1.0, "X", [1]), theta[1] / 2)])
+        d1 = eng.apply(x1, psi)
+        eng.scale(d1, -0.5j)
+        return psi, [d0, d1]
+
+    np.random.seed(1234)
+    x0 = np.random.uniform(0, 2 * np.pi, 2)
+    # the derivative states are consistent with finite differences of the state
+    psi, dps = state_and_derivatives(x0)
+    for k in range(2):
+        step = np.zeros(2)
+        step[k] = 1e-6
+        fd = (state_and_derivatives(x0 + step)[0] - state_and_derivatives(x0 - step)[0]).cpu().numpy() / 2e-6
+        assert np.max(np.abs(fd - dps[k].cpu().numpy())) < 1e-8
+    opt = qfe.plugins.GradientDescentOptimizer(maxiter=100, lambda_step=0.2, natural_gradient=natural, tol=1e-7, x0=x0, engine=eng)
+    value, params, info = opt.optimize(["\\theta_0", "\\theta_1"], hs, state_and_derivatives)
+    np.testing.assert_almost_equal(value, exact, decimal=4)
+    assert info["iterations"] <= 100 and len(info["energies"]) == info["iterations"] + 1
