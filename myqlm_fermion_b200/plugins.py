@@ -13,7 +13,8 @@ observable evaluations are done by libqfe.
 * ``SeqOptim.optimize``                                      <->  SeqOptim.optimize (sequential_optimization.py:104-146)
 * ``vqe_energy``                                             <->  VQE.fun (vqe.py:53-59)
 * ``AdaptVQE.run``                                           <->  AdaptVQEPlugin.run (adapt_vqe.py:143-240), state preparation on the device
-* ``qse_matrices``                                           <->  the H / S loops of the QSE helper (chemistry/qse.py:191-214)
+* ``qse_matrices``, ``apply_quantum_subspace_expansion``,
+  ``build_linear_pauli_expansion``                           <->  chemistry/qse.py:17-241
 * ``GradientDescentOptimizer``                               <->  GradientDescentOptimizer.optimize (naturalgradient/qfim_plugin.py:96-251)
 """
 
@@ -326,3 +327,21 @@ class AdaptVQE:
             "n_iters_optim": str(n_iters_optim),
         }
         return res
+
+
+def apply_quantum_subspace_expansion(hamiltonian: SpinHamiltonian, psi, expansion_operators: Sequence[SpinHamiltonian], engine=None, threshold: float = 1e-15,
+                                     return_matrices: bool = False):
+    """``apply_quantum_subspace_expansion`` (/root/reference/qat/fermion/chemistry/qse.py:17-135) for a device state: the lowest real
+    part of the generalised eigenvalues of (H^(s), S) built by ``qse_matrices``."""
+    import scipy.linalg
+
+    matrix_h, matrix_s = qse_matrices(hamiltonian, psi, expansion_operators, engine=engine, threshold=threshold)
+    e_qse = min(x.real for x in scipy.linalg.eig(matrix_h, matrix_s)[0])
+    return (e_qse, matrix_h, matrix_s) if return_matrices else e_qse
+
+
+def build_linear_pauli_expansion(pauli_gates: Sequence[str], nb_qubits: int) -> List[SpinHamiltonian]:
+    """First-order expansion operators: every listed Pauli letter on every qubit, letters outermost (qse.py:216-241)."""
+    from .hamiltonians import Term
+
+    return [SpinHamiltonian(nb_qubits, [Term(1.0, pauli, [qbit])]) for pauli in pauli_gates for qbit in range(nb_qubits)]

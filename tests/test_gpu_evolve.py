@@ -370,3 +370,33 @@ def test_gradient_descent_reaches_the_exact_energy_like_the_reference_test(eng, 
     value, params, info = opt.optimize(["\\theta_0", "\\theta_1"], hs, state_and_derivatives)
     np.testing.assert_almost_equal(value, exact, decimal=4)
     assert info["iterations"] <= 100 and len(info["energies"]) == info["iterations"] + 1
+
+
+def test_qse_on_the_vqe_state_of_the_reference_example(eng):
+    """tests/integration/test_qse.py: H = XX + YY + ZZ, ansatz RY(t0, 0) RY(t1, 1) RZ(t2, 1) CNOT(0, 1) optimised by SeqOptim from
+    [0, 0.5, 0] (10 cycles), expansion {1, ZZ}: the QSE energy is -3; and the linear Pauli expansion's matrices."""
+    import myqlm_fermion_b200 as qfe
+
+    T = qfe.Term
+    hs = qfe.SpinHamiltonian(2, [T(1, op, [0, 1]) for op in ["XX", "YY", "ZZ"]])
+    plan = eng.plan(hs.packed(eng))
+    cnot = [(T(1.0, "Z", [0]), -np.pi / 4), (T(1.0, "X", [1]), -np.pi / 4), (T(1.0, "ZX", [0, 1]), np.pi / 4)]
+
+    def state(p):
+        gates = [(T(1.0, "Y", [0]), p[0] / 2), (T(1.0, "Y", [1]), p[1] / 2), (T(1.0, "Z", [1]), p[2] / 2)] + cnot
+        x, z, _ = qfe.pack_terms(2, [g for g, _ in gates])
+        psi = eng.basis_state(2, 0)
+        eng.pauli_rotations(psi, x, z, [a for _, a in gates])
+        return psi
+
+    names = ["t0", "t1", "t2"]
+    e_vqe, params, _ = qfe.plugins.SeqOptim(ncycles=10, x0=[0, 0.5, 0]).optimize(names, lambda p: eng.energy(plan, state([p[k] for k in names])))
+    assert e_vqe <= -2.9
+    expansion = [qfe.SpinHamiltonian(2, [], 1.0), qfe.SpinHamiltonian(2, [T(1.0, "ZZ", [0, 1])])]
+    e_qse = qfe.plugins.apply_quantum_subspace_expansion(hs, state(params), expansion, engine=eng)
+    np.testing.assert_almost_equal(e_qse, -3.0)
+    e2, mh, ms = qfe.plugins.apply_quantum_subspace_expansion(hs, state(params), expansion, engine=eng, return_matrices=True)
+    assert e2 == e_qse and mh.shape == ms.shape == (2, 2) and abs(ms[0, 0] - 1) < 1e-12
+    ops = qfe.plugins.build_linear_pauli_expansion(["X", "Y", "Z", "Z", "I"], 1)
+    want = [np.array([[0, 1], [1, 0]]), np.array([[0, -1j], [1j, 0]]), np.array([[1, 0], [0, -1]]), np.array([[1, 0], [0, -1]]), np.eye(2)]
+    np.testing.assert_equal([o.get_matrix() for o in ops], [w.astype(np.complex128) for w in want])
