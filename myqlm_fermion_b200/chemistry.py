@@ -28,3 +28,29 @@ def get_cluster_ops(n_electrons: int, nqbits: Optional[int] = None, noons: Optio
     if n_electrons % 2 != 0:
         raise ValueError("Only even values of n_electrons are allowed.")
     return [FermionHamiltonian(nqbits, [Term(c, op, idx) for c, op, idx in terms]) for terms in uccsd_pool_fermion_terms(n_electrons, nqbits)]
+
+
+def construct_ucc_ansatz(cluster_ops, ket_hf: int, n_steps: int = 1, engine=None):
+    """State preparation of the UCC ansatz as ``construct_ucc_ansatz`` builds it (ucc.py:291-343): the Hartree-Fock determinant, then per
+    Trotter step the first-order slice of H_theta = sum_k theta_k (iT_k) with coeff = 1 / n_steps, i.e. prod_t exp(-i c_t P_t / n_steps)
+    over the merged Pauli terms of H_theta.  Returns ``theta -> device state`` (len(theta) = len(cluster_ops) * n_steps); ``cluster_ops``
+    are the spin-transformed cluster operators."""
+    from .engine import get_engine
+
+    eng = engine or get_engine()
+    nqbits = cluster_ops[0].nbqbits
+
+    def state(theta):
+        if len(theta) != len(cluster_ops) * n_steps:
+            raise ValueError(f"expected {len(cluster_ops) * n_steps} angles, got {len(theta)}")
+        psi = eng.basis_state(nqbits, ket_hf)
+        idx = 0
+        for _ in range(n_steps):
+            h_theta = None
+            for th, op in zip(theta[idx : idx + len(cluster_ops)], cluster_ops):
+                h_theta = float(th) * op if h_theta is None else h_theta + float(th) * op
+            eng.trotter_slice(h_theta, psi, coeff=1.0 / n_steps)
+            idx += len(cluster_ops)
+        return psi
+
+    return state

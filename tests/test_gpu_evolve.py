@@ -400,3 +400,27 @@ def test_qse_on_the_vqe_state_of_the_reference_example(eng):
     ops = qfe.plugins.build_linear_pauli_expansion(["X", "Y", "Z", "Z", "I"], 1)
     want = [np.array([[0, 1], [1, 0]]), np.array([[0, -1j], [1j, 0]]), np.array([[1, 0], [0, -1]]), np.array([[1, 0], [0, -1]]), np.eye(2)]
     np.testing.assert_equal([o.get_matrix() for o in ops], [w.astype(np.complex128) for w in want])
+
+
+def test_ucc_on_h2_reproduces_the_reference_energy_to_8_decimals(eng, golden_dir, goldens):
+    """tests/integration/test_integration_ucc.py:115-175 (test_more_basic): full H2 Hamiltonian in JW form, UCCSD cluster operators,
+    construct_ucc_ansatz on the Hartree-Fock state, COBYLA(tol=1e-15, maxiter=1000) -> -1.1372701746609022 to 8 decimals.  (The
+    reference starts from an MP2 guess; chemistry pre-processing is out of scope here and the search starts from zero.)"""
+    import scipy.optimize
+
+    import myqlm_fermion_b200 as qfe
+
+    d = qfe.load_molecule_npz(golden_dir / "h2_integrals.npz")
+    hpq, hpqrs = qfe.convert_to_h_integrals(d["one_body_integrals"], d["two_body_integrals"])
+    h = qfe.ElectronicStructureHamiltonian(hpq, hpqrs, constant_coeff=float(d["nuclear_repulsion"]))
+    h_sp = qfe.transform_to_jw_basis(h)
+    cluster_ops_sp = [qfe.transform_to_jw_basis(t) for t in qfe.get_cluster_ops(int(d["n_electrons"]), nqbits=h_sp.nbqbits)]
+    hf_init_sp = qfe.recode_integer(qfe.get_hf_ket(int(d["n_electrons"]), h_sp.nbqbits), qfe.get_jw_code(h_sp.nbqbits))
+    ansatz = qfe.construct_ucc_ansatz(cluster_ops_sp, hf_init_sp, engine=eng)
+    plan = eng.plan(h_sp.packed(eng))
+    res = scipy.optimize.minimize(lambda theta: eng.energy(plan, ansatz(theta)), x0=np.zeros(len(cluster_ops_sp)), tol=1e-15, method="COBYLA",
+                                  options={"maxiter": 1000})
+    np.testing.assert_almost_equal(res.fun, -1.1372701746609022, decimal=8)
+    g = goldens["scalars"].get("h2_ucc_vqe_energy")
+    if g is not None:
+        np.testing.assert_almost_equal(res.fun, g["value"], decimal=g["decimals"])
