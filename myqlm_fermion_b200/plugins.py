@@ -11,7 +11,7 @@ observable evaluations are done by libqfe.
 * ``AdaptVQEGradients``                                      <->  AdaptVQEPlugin._compute_commutators + the gradient loop
                                                                  (adapt_vqe.py:50-62, 181-195)
 * ``SeqOptim.optimize``                                      <->  SeqOptim.optimize (sequential_optimization.py:104-146)
-* ``vqe_energy``                                             <->  VQE.fun (vqe.py:53-59)
+* ``VQE``, ``vqe_energy``                                    <->  VQE and its cost function (vqe.py:13-62)
 * ``AdaptVQE.run``                                           <->  AdaptVQEPlugin.run (adapt_vqe.py:143-240), state preparation on the device
 * ``qse_matrices``, ``apply_quantum_subspace_expansion``,
   ``build_linear_pauli_expansion``                           <->  chemistry/qse.py:17-241
@@ -173,6 +173,15 @@ def vqe_energy(hamiltonian: SpinHamiltonian, state_routine: Callable, engine=Non
         return eng.energy(plan, state_routine(theta))
 
     return fun
+
+
+def VQE(hamiltonian: SpinHamiltonian, optimizer: Callable, state_routine: Callable, theta0, engine=None, n_shots=None):
+    """``VQE`` (/root/reference/qat/fermion/vqe.py:13-62): ``optimizer(fun, theta0) -> (theta, energy, nfev, trace)`` minimises
+    theta -> <psi(theta)|H|psi(theta)>, with ``state_routine(theta)`` returning the device state the reference would prepare from
+    ``ansatz_routine(theta)``.  Returns (energy, theta, None, None) like the reference; ``n_shots`` is accepted and ignored (exact
+    expectation values, the reference's nbshots = 0)."""
+    theta, energy, _, _ = optimizer(vqe_energy(hamiltonian, state_routine, engine=engine), theta0)
+    return energy, theta, None, None
 
 
 def qse_matrices(hamiltonian: SpinHamiltonian, psi, expansion_operators: Sequence[SpinHamiltonian], engine=None, threshold: float = 1e-15):

@@ -424,3 +424,39 @@ def test_ucc_on_h2_reproduces_the_reference_energy_to_8_decimals(eng, golden_dir
     g = goldens["scalars"].get("h2_ucc_vqe_energy")
     if g is not None:
         np.testing.assert_almost_equal(res.fun, g["value"], decimal=g["decimals"])
+
+
+def test_vqe_function_on_the_reference_examples(eng):
+    """tests/integration/test_integration_vqe.py:33-73: one- and two-qubit Hamiltonians from integrals through transform_to_jw_basis,
+    RY / RX ansatz circuits, a derivative-free optimiser with the reference's (theta, energy, nfev, trace) return convention (the
+    reference's SPSA lives in the absent qat.vsolve; Nelder-Mead plays its role), energies to 3 decimals / 5e-3."""
+    import random
+
+    import scipy.optimize
+
+    import myqlm_fermion_b200 as qfe
+
+    T = qfe.Term
+
+    def optimizer(fun, theta0):
+        res = scipy.optimize.minimize(fun, theta0, method="Nelder-Mead", options={"xatol": 1e-7, "fatol": 1e-9, "maxiter": 2000})
+        return res.x, float(res.fun), res.nfev, []
+
+    def rotations(n, gates):
+        x, z, _ = qfe.pack_terms(n, [g for g, _ in gates])
+        psi = eng.basis_state(n, 0)
+        eng.pauli_rotations(psi, x, z, [a for _, a in gates])
+        return psi
+
+    random.seed(7)
+    hamilt_sp = qfe.transform_to_jw_basis(qfe.ElectronicStructureHamiltonian(hpq=np.ones((1, 1)), hpqrs=np.zeros((1, 1, 1, 1))))
+    energy, theta, _, _ = qfe.plugins.VQE(hamilt_sp, optimizer, lambda x: rotations(1, [(T(1.0, "Y", [0]), x[0] / 2)]),
+                                          np.array([random.random() * 2 * np.pi]), engine=eng)
+    assert abs(energy - 0.0) < 1e-3
+    hpq = np.array([[-3.0, 2.0], [2.0, -3.0]])
+    hamiltonian = qfe.ElectronicStructureHamiltonian(hpq, np.zeros((2, 2, 2, 2)))
+    want = min(np.linalg.eigvalsh(hamiltonian.get_matrix()))
+    energy, theta, _, _ = qfe.plugins.VQE(qfe.transform_to_jw_basis(hamiltonian), optimizer,
+                                          lambda x: rotations(2, [(T(1.0, "Y", [0]), x[0] / 2), (T(1.0, "X", [1]), x[1] / 2)]),
+                                          np.array([random.random() * 2 * np.pi, random.random() * 2 * np.pi]), engine=eng)
+    assert abs(want + 6.0) < 1e-12 and abs(energy - want) < 5e-3  # |11> (both modes filled) is a product state the ansatz reaches
