@@ -138,28 +138,51 @@ __global__ void __launch_bounds__(VT) fill_random_kernel(typename C2<real_t>::ty
     }
 }
 
-// product state  (x)_q (alpha_q |0> + beta_q |1>), qubit q <-> bit n-1-q of the full index
+// product state  (x)_q (alpha_q |0> + beta_q |1>), qubit q <-> bit n-1-q of the full index.  The factor of the low PS_LOW_BITS qubits is
+// a shared-memory table built once per CTA; a CTA writes blocks of 2^PS_LOW_BITS consecutive amplitudes = (factor of the high qubits,
+// one product chain per thread and block) x table: about three complex multiplications per amplitude instead of n, so the
+// kernel runs at the HBM write rate.
+constexpr int PS_LOW_BITS = 11;
 template <typename real_t>
 __global__ void __launch_bounds__(VT) product_state_kernel(typename C2<real_t>::type* __restrict__ x, int n_local, uint64_t shard, int n,
                                                             const double* __restrict__ ab) {
     __shared__ double s_ab[4 * 64];
+    __shared__ double2 s_lo[1 << PS_LOW_BITS];
     for (int i = threadIdx.x; i < 4 * n; i += VT) s_ab[i] = ab[i];
     __syncthreads();
-    const int64_t n_amps = int64_t(1) << n_local;
-    for (int64_t i = (int64_t)blockIdx.x * VT + threadIdx.x; i < n_amps; i += (int64_t)gridDim.x * VT) {
-        const uint64_t b = (shard << n_local) | (uint64_t)i;
+    const int L = n_local < PS_LOW_BITS ? n_local : PS_LOW_BITS;
+    const int n_lo = 1 << L;
+    for (int j = threadIdx.x; j < n_lo; j += VT) {
         double re = 1.0, im = 0.0;
-        for (int q = 0; q < n; ++q) {
+        for (int q = n - L; q < n; ++q) {
+            const int bit = (j >> (n - 1 - q)) & 1;
+            const double fr = s_ab[4 * q + 2 * bit], fi = s_ab[4 * q + 2 * bit + 1];
+            const double t = re * fr - im * fi;
+            im = re * fi + im * fr;
+            re = t;
+        }
+        s_lo[j] = make_double2(re, im);
+    }
+    __syncthreads();
+    const int64_t n_blocks = (int64_t(1) << n_local) >> L;
+    for (int64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+        const uint64_t b = (shard << n_local) | ((uint64_t)blk << L);
+        double re = 1.0, im = 0.0;
+        for (int q = 0; q < n - L; ++q) {
             const int bit = (int)((b >> (n - 1 - q)) & 1ull);
             const double fr = s_ab[4 * q + 2 * bit], fi = s_ab[4 * q + 2 * bit + 1];
             const double t = re * fr - im * fi;
             im = re * fi + im * fr;
             re = t;
         }
-        typename C2<real_t>::type o;
-        o.x = (real_t)re;
-        o.y = (real_t)im;
-        x[i] = o;
+        typename C2<real_t>::type* __restrict__ out = x + (blk << L);
+        for (int j = threadIdx.x; j < n_lo; j += VT) {
+            const double2 f = s_lo[j];
+            typename C2<real_t>::type o;
+            o.x = (real_t)(re * f.x - im * f.y);
+            o.y = (real_t)(re * f.y + im * f.x);
+            out[j] = o;
+        }
     }
 }
 

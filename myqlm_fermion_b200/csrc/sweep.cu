@@ -682,9 +682,13 @@ __global__ void __launch_bounds__(NTH, NT_MAX / NTH) tile_sweep_kernel(const __g
             for (uint32_t idx = 8u * tid; idx < tile_amps; idx += 8u * NT)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(ket + (nbase | s_nat_off[idx & 127] | s_nat_off[128 + (idx >> 7)])));
         }
+        // y += ...: the tile's lines of y travel to L2 while the groups are processed, for the read-modify-write that ends the tile
+        if (MODE == MODE_APPLY && a.accumulate && a.prefetch_dist > 0)
+            for (uint32_t idx = 8u * tid; idx < tile_amps; idx += 8u * NT)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(yout + (base | s_nat_off[idx & 127] | s_nat_off[128 + (idx >> 7)])));
 
+        real_t acc_re[R], acc_im[R];
         if (active) {
-            real_t acc_re[R], acc_im[R];
             cplx_t own[R];
             if (MODE == MODE_APPLY) {
 #pragma unroll
@@ -721,21 +725,49 @@ __global__ void __launch_bounds__(NTH, NT_MAX / NTH) tile_sweep_kernel(const __g
                 else
                     process_range<real_t, CPLX, MODE, KIND_RUNS | KIND_XROW, PLANE>(tile, terms, s_hdr, s_acc_warp, g0, g1, t0, w0, jhi, half, own, acc_re, acc_im, e_re, e_im);
             }
-            if (MODE == MODE_APPLY) {
+        }
+        if (MODE == MODE_APPLY) {
+            // the result leaves through the tile, in the natural order it was staged in: 128 B contiguous per 8 threads, and the 16
+            // loads of y a thread needs for y += ... are in flight together
+            __syncthreads();  // every partner row has been read
+            if (active) {
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    const uint32_t j = jhi | (uint32_t)r;
-                    const uint64_t gidx = base | s_loc_off[j & 127] | s_loc_off[128 + (j >> 7)];
-                    cplx_t y;
+                    cplx_t o;
+                    o.x = acc_re[r];
+                    o.y = acc_im[r];
+                    tile[(uint32_t)r * PLANE + w0] = o;
+                }
+            }
+            __syncthreads();
+            if (tile_amps == R * NT) {
+#pragma unroll
+                for (int h = 0; h < R; h += R / 2) {  // two batches of 8 loads in flight
+                    cplx_t v[R / 2];
                     if (a.accumulate) {
-                        y = yout[gidx];
-                        y.x += acc_re[r];
-                        y.y += acc_im[r];
-                    } else {
-                        y.x = acc_re[r];
-                        y.y = acc_im[r];
+#pragma unroll
+                        for (int u = 0; u < R / 2; ++u) v[u] = yout[base | off_lo | s_nat_off[128 + ((tid + (h + u) * NT) >> 7)]];
                     }
-                    yout[gidx] = y;
+#pragma unroll
+                    for (int u = 0; u < R / 2; ++u) {
+                        cplx_t o = tile[tile_word<PLANE>(loc_lo | s_nat_loc[128 + ((tid + (h + u) * NT) >> 7)])];
+                        if (a.accumulate) {
+                            o.x += v[u].x;
+                            o.y += v[u].y;
+                        }
+                        yout[base | off_lo | s_nat_off[128 + ((tid + (h + u) * NT) >> 7)]] = o;
+                    }
+                }
+            } else {
+                for (uint32_t idx = tid; idx < tile_amps; idx += NT) {
+                    const uint64_t gidx = base | s_nat_off[idx & 127] | s_nat_off[128 + (idx >> 7)];
+                    cplx_t o = tile[tile_word<PLANE>(s_nat_loc[idx & 127] | s_nat_loc[128 + (idx >> 7)])];
+                    if (a.accumulate) {
+                        const cplx_t y = yout[gidx];
+                        o.x += y.x;
+                        o.y += y.y;
+                    }
+                    yout[gidx] = o;
                 }
             }
         }
