@@ -468,7 +468,7 @@ int build_plan(const TermView& t, int n_local, int shard, const PlanLimits& lim,
                         ++nt_emit;
                     }
                     out.g_hdr.push_back(gi.xl | ((uint32_t)nt_emit << HDR_NT_SHIFT) | (gi.imag ? HDR_IMAG : 0u));
-                    out.g_hdr.push_back(0u);
+                    out.g_hdr.push_back(t_local);  // first staged term of the group: lets a CTA start in the middle of a range
                     out.g_slot.push_back(g.slot);
                     done[gi.gi] = 1;
                     --left;

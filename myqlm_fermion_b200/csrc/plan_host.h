@@ -99,7 +99,7 @@ struct PlanHost {
     bool use_tiles = false;
     std::vector<ClassHost> classes;  // ascending x_hi
     std::vector<SweepHost> sweeps;
-    // tiled layout (sweep order); two header words per group, see the HDR_* constants
+    // tiled layout (sweep order); two header words per group: the HDR_* fields, then the sweep-local index of its first staged term
     std::vector<uint32_t> g_hdr;
     std::vector<int32_t> g_slot;
     std::vector<uint32_t> r_desc;  // two words per range

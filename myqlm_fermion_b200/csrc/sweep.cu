@@ -76,6 +76,9 @@ struct SweepArgs {
     int k, n_runs;
     int same_tile, accumulate;
     int prefetch_dist;  // tiles ahead that go to L2 while the current one is processed (0: off)
+    int split;          // CTAs that share one tile, each taking a slice of the groups of every range (shards with fewer tiles than SMs)
+    int pstride;        // BATCH: partials of group g start at g * pstride
+    unsigned long long slab_amps;  // APPLY with split > 1: CTA part p writes its partial result at out_vec + p * slab_amps
     unsigned long long n_tiles;
     unsigned long long ket_xor;
     uint8_t run_pos[PLAN_MAX_RUNS];
@@ -608,7 +611,18 @@ __global__ void __launch_bounds__(NTH, NT_MAX / NTH) tile_sweep_kernel(const __g
 
     // ---- once per CTA: tile-independent tables ------------------------------------------------
     for (int g = tid; g < nG; g += NT) s_hdr[g] = make_uint2(a.g_hdr[2 * g], a.g_hdr[2 * g + 1]);
-    for (int g = tid; g < nR; g += NT) s_rng[g] = make_uint2(a.r_desc[2 * g], a.r_desc[2 * g + 1]);
+    for (int g = tid; g < nR; g += NT) {
+        uint2 d = make_uint2(a.r_desc[2 * g], a.r_desc[2 * g + 1]);
+        if (a.split > 1) {
+            // small shards: a.split CTAs stage the same tile; this one keeps its slice of the groups of every range (possibly none)
+            const uint32_t split = (uint32_t)a.split, part = blockIdx.x % split;
+            const uint32_t g0 = d.x & 0xffffu, len = (d.x >> 16) - g0;
+            const uint32_t gs = g0 + len * part / split, ge = g0 + len * (part + 1u) / split;
+            d.x = gs | (ge << 16);
+            if (gs < ge) d.y = (d.y & ~0xffffu) | a.g_hdr[2 * gs + 1];  // second header word: the group's first staged term
+        }
+        s_rng[g] = d;
+    }
     for (int i = tid; i < PLAN_TABLE; i += NT) {
         s_nat_off[i] = a.nat_off[i];
         s_loc_off[i] = a.loc_off[i];
@@ -636,7 +650,11 @@ __global__ void __launch_bounds__(NTH, NT_MAX / NTH) tile_sweep_kernel(const __g
     const uint32_t w0 = (uint32_t)tid;
     double e_re = 0.0, e_im = 0.0;
 
-    for (unsigned long long tile_id = blockIdx.x; tile_id < a.n_tiles; tile_id += gridDim.x) {
+    // small shards: a.split CTAs stage the same tile (their range descriptors differ, see above)
+    // (a.split sits in the constant bank; nothing of this is kept in registers across the group loops)
+    if (MODE == MODE_APPLY) yout += (size_t)(blockIdx.x % (uint32_t)a.split) * a.slab_amps;
+
+    for (unsigned long long tile_id = blockIdx.x / (uint32_t)a.split; tile_id < a.n_tiles; tile_id += gridDim.x / (uint32_t)a.split) {
         // shard position of the tile: deposit the tile number into the bits outside the tile mask
         uint64_t base = 0;
         {
@@ -670,9 +688,9 @@ __global__ void __launch_bounds__(NTH, NT_MAX / NTH) tile_sweep_kernel(const __g
         }
         __syncthreads();
         // next tile of this CTA -> L2 while this one is processed (two 128 B lines per thread)
-        if (a.prefetch_dist > 0 && tile_id + (unsigned long long)a.prefetch_dist * gridDim.x < a.n_tiles) {
+        if (a.prefetch_dist > 0 && tile_id + (unsigned long long)a.prefetch_dist * (gridDim.x / (uint32_t)a.split) < a.n_tiles) {
             uint64_t nbase = 0;
-            unsigned long long rest = tile_id + (unsigned long long)a.prefetch_dist * gridDim.x;
+            unsigned long long rest = tile_id + (unsigned long long)a.prefetch_dist * (gridDim.x / (uint32_t)a.split);
             for (int r = 0; r < a.n_runs; ++r) {
                 const int len = a.run_len[r];
                 nbase |= (rest & ((1ull << len) - 1ull)) << a.run_pos[r];
@@ -784,7 +802,7 @@ __global__ void __launch_bounds__(NTH, NT_MAX / NTH) tile_sweep_kernel(const __g
                 s.x += s_acc[w * nG + g].x;
                 s.y += s_acc[w * nG + g].y;
             }
-            a.partials[(size_t)g * gridDim.x + blockIdx.x] = s;
+            a.partials[(size_t)g * a.pstride + blockIdx.x] = s;
         }
     }
 }
@@ -876,6 +894,26 @@ __global__ void __launch_bounds__(128) reduce_partials(const double2* __restrict
     if (lane == 0) vals[r] = make_double2(sx, sy);
 }
 
+// y (+)= sum_p slab[p], fixed order: ends an APPLY class whose tiles were shared by several CTAs
+template <typename cplx_t>
+__global__ void __launch_bounds__(256) combine_slabs(const cplx_t* __restrict__ slabs, int n_parts, int64_t n_amps, cplx_t* __restrict__ y, int accumulate) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_amps; i += (int64_t)gridDim.x * blockDim.x) {
+        cplx_t v;
+        if (accumulate) {
+            v = y[i];
+        } else {
+            v.x = 0;
+            v.y = 0;
+        }
+        for (int p = 0; p < n_parts; ++p) {
+            const cplx_t w = slabs[(size_t)p * n_amps + i];
+            v.x += w.x;
+            v.y += w.y;
+        }
+        y[i] = v;
+    }
+}
+
 int reduce_to_vals(qfe_ctx* ctx, const double2* partials, int n_ranges, int n_blocks, double2* vals) {
     reduce_partials<<<(n_ranges + 3) / 4, 128, 0, ctx->stream>>>(partials, n_ranges, n_blocks, vals);
     ctx->launches++;
@@ -914,15 +952,32 @@ static int find_class(const qfe_plan* p, int x_hi) {
 
 // CTA size and grid of a sweep: 2^13-amplitude tiles = one CTA of 512 threads per SM, smaller tiles = two CTAs of 256 threads
 static int sweep_threads(int k) { return k >= PLAN_MAX_TILE_BITS ? NT_MAX : NT_MAX / 2; }
-static int sweep_grid(const qfe_ctx* ctx, const SweepHost& sw) {
-    return (int)std::min<int64_t>(sw.n_tiles, (int64_t)ctx->sm_count * (NT_MAX / sweep_threads(sw.k)));
+static int64_t sweep_capacity(const qfe_ctx* ctx, const SweepHost& sw) { return (int64_t)ctx->sm_count * (NT_MAX / sweep_threads(sw.k)); }
+// A shard with fewer tiles than the GPU has CTA slots: up to SWEEP_MAX_SPLIT CTAs stage the same tile and share the groups of each of
+// its ranges (a tile takes ~20 us to work through alone, whatever the register size).  QFE_SPLIT=1 turns this off (development knob).
+constexpr int SWEEP_MAX_SPLIT = 16;
+static int sweep_split(const qfe_ctx* ctx, const SweepHost& sw, bool any_group_count = false) {
+    static const int cap_env = [] {
+        const char* e = getenv("QFE_SPLIT");
+        return e ? std::max(1, atoi(e)) : SWEEP_MAX_SPLIT;
+    }();
+    const int64_t cap = sweep_capacity(ctx, sw);
+    if (sw.n_tiles * 2 > cap || (!any_group_count && sw.group_end - sw.group_begin < 2)) return 1;
+    return (int)std::min<int64_t>(cap / sw.n_tiles, std::min(cap_env, SWEEP_MAX_SPLIT));
+}
+static int sweep_grid(const qfe_ctx* ctx, const SweepHost& sw, int split) {
+    return split > 1 ? (int)(sw.n_tiles * split) : (int)std::min<int64_t>(sw.n_tiles, sweep_capacity(ctx, sw));
 }
 
 template <typename real_t, bool CPLX, int MODE, int NTH>
 static int launch_tile_n(qfe_ctx* ctx, const SweepArgs& args, int grid) {
     auto kern = tile_sweep_kernel<real_t, CPLX, MODE, NTH>;
     constexpr size_t smem = Geo<NTH>::SM_TOTAL;
-    QFE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static int attr_device = -1;  // once per instantiation (and again if another device's context comes by)
+    if (attr_device != ctx->device) {
+        QFE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_device = ctx->device;
+    }
     kern<<<grid, NTH, smem, ctx->stream>>>(args);
     ctx->launches++;
     QFE_CUDA(cudaGetLastError());
@@ -966,10 +1021,12 @@ static void fill_sweep_args(const qfe_plan* p, const SweepHost& s, int dtype, Sw
     a.n_groups = s.group_end - s.group_begin;
     a.n_terms = (int)(s.term_end - s.term_begin);
     a.k = s.k;
-    {
+    static const int prefetch_dist = [] {
         const char* pd = getenv("QFE_PREFETCH_DIST");  // development knob
-        a.prefetch_dist = pd ? atoi(pd) : 1;
-    }
+        return pd ? atoi(pd) : 1;
+    }();
+    a.prefetch_dist = prefetch_dist;
+    a.split = 1;
     a.n_runs = s.n_runs;
     a.n_tiles = (unsigned long long)s.n_tiles;
     a.ket_xor = s.ket_xor;
@@ -1025,13 +1082,14 @@ static int run_class_reduce(qfe_ctx* ctx, const qfe_plan* p, int ci, const void*
     double2* d_vals = ctx->result.as<double2>();
     int64_t vpos = 0;
     if (tiles) {
-        size_t max_partials = 1;
-        for (int si = cls.sweep_begin; si < cls.sweep_end; ++si) {
-            const SweepHost& sw = p->h.sweeps[si];
-            const size_t grid = (size_t)sweep_grid(ctx, sw);
-            max_partials = std::max(max_partials, grid * (size_t)(batch ? sw.group_end - sw.group_begin : 1));
-        }
-        QFE_TRY(ctx->partials.reserve(sizeof(double2) * max_partials));
+        // every value (sweep, or group of a sweep in BATCH mode) owns one row of `row` per-CTA partials; rows of sweeps with a smaller
+        // grid keep their zeros, and ONE fixed-order reduction ends the class
+        size_t row = 1;
+        for (int si = cls.sweep_begin; si < cls.sweep_end; ++si)
+            if (mine(si)) row = std::max(row, (size_t)sweep_grid(ctx, p->h.sweeps[si], sweep_split(ctx, p->h.sweeps[si])));
+        QFE_REQUIRE(n_vals <= INT32_MAX && row <= INT32_MAX, QFE_ERR_ARG, "too many values in one class");
+        QFE_TRY(ctx->partials.reserve(sizeof(double2) * row * (size_t)n_vals));
+        QFE_CUDA(cudaMemsetAsync(ctx->partials.p, 0, sizeof(double2) * row * (size_t)n_vals, s));
         for (int si = cls.sweep_begin; si < cls.sweep_end; ++si) {
             if (!mine(si)) continue;
             const SweepHost& sw = p->h.sweeps[si];
@@ -1041,19 +1099,19 @@ static int run_class_reduce(qfe_ctx* ctx, const qfe_plan* p, int ci, const void*
             a.ket = ket;
             a.bra = bra;
             a.same_tile = (bra == ket && sw.ket_xor == 0) ? 1 : 0;
-            const int grid = sweep_grid(ctx, sw);
+            a.split = sweep_split(ctx, sw);
+            a.pstride = (int)row;
+            const int grid = sweep_grid(ctx, sw, a.split);
             const int n_ranges = batch ? a.n_groups : 1;
-            a.partials = ctx->partials.as<double2>();
+            a.partials = ctx->partials.as<double2>() + (size_t)vpos * row;
             if (batch)
                 QFE_TRY(launch_tile_d<MODE_BATCH>(ctx, a, grid, sw.complex_w, dtype));
             else
                 QFE_TRY(launch_tile_d<MODE_EXPECT>(ctx, a, grid, sw.complex_w, dtype));
-            reduce_partials<<<(n_ranges + 3) / 4, 128, 0, s>>>(a.partials, n_ranges, grid, d_vals + vpos);
-            ctx->launches++;
-            QFE_CUDA(cudaGetLastError());
             for (int g = 0; g < n_ranges; ++g) val_slot.push_back(batch ? p->h.g_slot[sw.group_begin + g] : 0);
             vpos += n_ranges;
         }
+        QFE_TRY(reduce_to_vals(ctx, ctx->partials.as<double2>(), (int)n_vals, (int)row, d_vals));
     } else {
         DirectArgs a;
         memset(&a, 0, sizeof(a));
@@ -1269,6 +1327,10 @@ int qfe_apply_class(qfe_ctx* ctx, const qfe_plan* p, int x_hi, const void* ket, 
     const bool tiles = p->h.use_tiles && !p->force_direct;
     if (tiles) {
         if (cls.sweep_begin == cls.sweep_end && !accumulate) QFE_CUDA(cudaMemsetAsync(y, 0, bytes, ctx->stream));
+        // small shards: the CTAs that share a tile leave their partial results in slabs, summed into y in a fixed order at the end
+        int split = cls.sweep_begin < cls.sweep_end ? SWEEP_MAX_SPLIT : 1;
+        for (int si = cls.sweep_begin; si < cls.sweep_end; ++si) split = std::min(split, sweep_split(ctx, p->h.sweeps[si], true));  // one split for the class
+        if (split > 1) QFE_TRY(ctx->slabs.reserve(bytes * (size_t)split));
         for (int si = cls.sweep_begin; si < cls.sweep_end; ++si) {
             const SweepHost& sw = p->h.sweeps[si];
             SweepArgs a;
@@ -1276,10 +1338,27 @@ int qfe_apply_class(qfe_ctx* ctx, const qfe_plan* p, int x_hi, const void* ket, 
             fill_sweep_args(p, sw, dtype, a);
             a.ket = ket;
             a.bra = ket;
-            a.out_vec = y;
             a.same_tile = 0;
-            a.accumulate = (si == cls.sweep_begin) ? (accumulate ? 1 : 0) : 1;
-            QFE_TRY(launch_tile_d<MODE_APPLY>(ctx, a, sweep_grid(ctx, sw), sw.complex_w, dtype));
+            a.split = split;
+            if (split > 1) {
+                a.out_vec = ctx->slabs.p;
+                a.slab_amps = 1ull << p->h.n_local;
+                a.accumulate = si != cls.sweep_begin;
+            } else {
+                a.out_vec = y;
+                a.accumulate = (si == cls.sweep_begin) ? (accumulate ? 1 : 0) : 1;
+            }
+            QFE_TRY(launch_tile_d<MODE_APPLY>(ctx, a, sweep_grid(ctx, sw, split), sw.complex_w, dtype));
+        }
+        if (split > 1) {
+            const int64_t n_amps = int64_t(1) << p->h.n_local;
+            const int gx = (int)std::min<int64_t>((n_amps + 255) / 256, (int64_t)ctx->sm_count * 8);
+            if (dtype == QFE_C128)
+                combine_slabs<double2><<<gx, 256, 0, ctx->stream>>>(ctx->slabs.as<double2>(), split, n_amps, (double2*)y, accumulate ? 1 : 0);
+            else
+                combine_slabs<float2><<<gx, 256, 0, ctx->stream>>>(ctx->slabs.as<float2>(), split, n_amps, (float2*)y, accumulate ? 1 : 0);
+            ctx->launches++;
+            QFE_CUDA(cudaGetLastError());
         }
     } else {
         DirectArgs a;

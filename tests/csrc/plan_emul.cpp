@@ -112,6 +112,7 @@ extern "C" int plan_emul_run(int n, int64_t T, const uint64_t* x, const uint64_t
                             const uint32_t xl = ha & HDR_XL_MASK;
                             const int nt = (int)((ha >> HDR_NT_SHIFT) & HDR_NT_MASK);
                             const bool imag = ha & HDR_IMAG;
+                            if ((int64_t)p.g_hdr[2 * g + 1] != tb - s.term_begin) return 28;  // second word: first staged term of the group
                             if (skipbit && ((31 - __builtin_clz(xl)) != (int)skipbit || imag)) return 13;  // the skip bit is the top X bit
                             if (((kind & KIND_XROW) != 0) != ((xl & 15u) != 0)) return 21;  // X bits on register rows are flagged
                             cplx w(0.0, 0.0);
