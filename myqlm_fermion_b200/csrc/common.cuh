@@ -80,6 +80,8 @@ struct qfe_ctx {
     qfe::DevBuf partials;   // per-block partial sums of the sweep kernels
     qfe::DevBuf result;     // final reduced scalars
     qfe::DevBuf hostvec;    // device landing buffer of qfe_expectation_host
+    cudaStream_t copy_stream = nullptr;      // upload stream of qfe_expectation_host
+    std::vector<cudaEvent_t> copy_events;
     qfe::DevBuf slabs;      // per-part partial results of APPLY sweeps whose tiles are shared by several CTAs (small shards)
     void* pinned = nullptr; // small pinned host buffer for scalar read-back
     size_t pinned_bytes = 0;

@@ -79,7 +79,7 @@ struct SweepArgs {
     int split;          // CTAs that share one tile, each taking a slice of the groups of every range (shards with fewer tiles than SMs)
     int pstride;        // BATCH: partials of group g start at g * pstride
     unsigned long long slab_amps;  // APPLY with split > 1: CTA part p writes its partial result at out_vec + p * slab_amps
-    unsigned long long n_tiles;
+    unsigned long long tile_begin, n_tiles;  // the launch covers tiles [tile_begin, n_tiles)
     unsigned long long ket_xor;
     uint8_t run_pos[PLAN_MAX_RUNS];
     uint8_t run_len[PLAN_MAX_RUNS];
@@ -654,7 +654,7 @@ __global__ void __launch_bounds__(NTH, NT_MAX / NTH) tile_sweep_kernel(const __g
     // (a.split sits in the constant bank; nothing of this is kept in registers across the group loops)
     if (MODE == MODE_APPLY) yout += (size_t)(blockIdx.x % (uint32_t)a.split) * a.slab_amps;
 
-    for (unsigned long long tile_id = blockIdx.x / (uint32_t)a.split; tile_id < a.n_tiles; tile_id += gridDim.x / (uint32_t)a.split) {
+    for (unsigned long long tile_id = a.tile_begin + blockIdx.x / (uint32_t)a.split; tile_id < a.n_tiles; tile_id += gridDim.x / (uint32_t)a.split) {
         // shard position of the tile: deposit the tile number into the bits outside the tile mask
         uint64_t base = 0;
         {
@@ -1028,6 +1028,7 @@ static void fill_sweep_args(const qfe_plan* p, const SweepHost& s, int dtype, Sw
     a.prefetch_dist = prefetch_dist;
     a.split = 1;
     a.n_runs = s.n_runs;
+    a.tile_begin = 0;
     a.n_tiles = (unsigned long long)s.n_tiles;
     a.ket_xor = s.ket_xor;
     memcpy(a.run_pos, s.run_pos, sizeof(a.run_pos));
@@ -1061,8 +1062,18 @@ static void fill_sweep_args(const qfe_plan* p, const SweepHost& s, int dtype, Sw
 // (EXPECT: one value per sweep; BATCH: one per group, sweep order).
 // part / n_parts: only the sweeps si with (si - first sweep of the class) % n_parts == part run (the direct kernel, which has no
 // sweeps, runs in part 0 only): the parts of a class add up to the whole class.
+// Upload pipeline of qfe_expectation_host: the state arrives in `chunks` equal pieces (its top qubits select the piece); a sweep
+// whose tile leaves those qubits alone can run on a piece as soon as it has landed, so the first sweeps hide the host->device copy.
+struct UploadPipe {
+    int chunks = 1;
+    int max_early = 0;                   // sweeps that run piece by piece
+    std::vector<cudaEvent_t> ready;      // ready[c]: piece c is in device memory
+    int (*issue_copy)(void*, int) = nullptr;  // enqueues the copy of piece c on the copy stream and records ready[c]
+    void* cookie = nullptr;
+};
+
 static int run_class_reduce(qfe_ctx* ctx, const qfe_plan* p, int ci, const void* bra, const void* ket, int dtype, int part, int n_parts,
-                            std::vector<double>& host_vals, std::vector<int32_t>& val_slot) {
+                            std::vector<double>& host_vals, std::vector<int32_t>& val_slot, const UploadPipe* pipe = nullptr) {
     const ClassHost& cls = p->h.classes[ci];
     const bool batch = p->batch;
     const bool tiles = p->h.use_tiles && !p->force_direct;
@@ -1071,9 +1082,24 @@ static int run_class_reduce(qfe_ctx* ctx, const qfe_plan* p, int ci, const void*
     val_slot.clear();
     int64_t n_vals = 0;
     auto mine = [&](int si) { return (si - cls.sweep_begin) % n_parts == part; };
+    // sweeps that run piece by piece while the state is uploaded (EXPECT on the state itself only)
+    std::vector<char> early(cls.sweep_end - cls.sweep_begin, 0);
+    int n_early = 0;
+    if (pipe && tiles && !batch && bra == ket && pipe->chunks > 1) {
+        int lc = 0;
+        while ((1 << lc) < pipe->chunks) ++lc;
+        const uint64_t top = ((uint64_t(1) << lc) - 1) << (p->h.n_local - lc);
+        for (int si = cls.sweep_begin; si < cls.sweep_end && n_early < pipe->max_early; ++si) {
+            const SweepHost& sw = p->h.sweeps[si];
+            if (mine(si) && sw.ket_xor == 0 && (sw.tile_mask & top) == 0 && sw.n_tiles >= (int64_t)pipe->chunks * ctx->sm_count) {
+                early[si - cls.sweep_begin] = 1;
+                ++n_early;
+            }
+        }
+    }
     if (tiles) {
         for (int si = cls.sweep_begin; si < cls.sweep_end; ++si)
-            if (mine(si)) n_vals += batch ? (p->h.sweeps[si].group_end - p->h.sweeps[si].group_begin) : 1;
+            if (mine(si)) n_vals += batch ? (p->h.sweeps[si].group_end - p->h.sweeps[si].group_begin) : (early[si - cls.sweep_begin] ? pipe->chunks : 1);
     } else {
         n_vals = part != 0 ? 0 : (batch ? (cls.dgroup_end - cls.dgroup_begin) : 1);
     }
@@ -1090,8 +1116,7 @@ static int run_class_reduce(qfe_ctx* ctx, const qfe_plan* p, int ci, const void*
         QFE_REQUIRE(n_vals <= INT32_MAX && row <= INT32_MAX, QFE_ERR_ARG, "too many values in one class");
         QFE_TRY(ctx->partials.reserve(sizeof(double2) * row * (size_t)n_vals));
         QFE_CUDA(cudaMemsetAsync(ctx->partials.p, 0, sizeof(double2) * row * (size_t)n_vals, s));
-        for (int si = cls.sweep_begin; si < cls.sweep_end; ++si) {
-            if (!mine(si)) continue;
+        auto launch = [&](int si, int64_t tile_begin, int64_t tile_end) -> int {
             const SweepHost& sw = p->h.sweeps[si];
             SweepArgs a;
             memset(&a, 0, sizeof(a));
@@ -1101,7 +1126,10 @@ static int run_class_reduce(qfe_ctx* ctx, const qfe_plan* p, int ci, const void*
             a.same_tile = (bra == ket && sw.ket_xor == 0) ? 1 : 0;
             a.split = sweep_split(ctx, sw);
             a.pstride = (int)row;
-            const int grid = sweep_grid(ctx, sw, a.split);
+            a.tile_begin = (unsigned long long)tile_begin;
+            a.n_tiles = (unsigned long long)tile_end;
+            const int grid = tile_end - tile_begin == sw.n_tiles ? sweep_grid(ctx, sw, a.split)
+                                                                 : (int)std::min<int64_t>(tile_end - tile_begin, sweep_capacity(ctx, sw));
             const int n_ranges = batch ? a.n_groups : 1;
             a.partials = ctx->partials.as<double2>() + (size_t)vpos * row;
             if (batch)
@@ -1110,7 +1138,21 @@ static int run_class_reduce(qfe_ctx* ctx, const qfe_plan* p, int ci, const void*
                 QFE_TRY(launch_tile_d<MODE_EXPECT>(ctx, a, grid, sw.complex_w, dtype));
             for (int g = 0; g < n_ranges; ++g) val_slot.push_back(batch ? p->h.g_slot[sw.group_begin + g] : 0);
             vpos += n_ranges;
+            return QFE_OK;
+        };
+        if (pipe && pipe->chunks > 1) {
+            for (int c = 0; c < pipe->chunks; ++c) {
+                QFE_TRY(pipe->issue_copy(pipe->cookie, c));
+                QFE_CUDA(cudaStreamWaitEvent(s, pipe->ready[c], 0));
+                for (int si = cls.sweep_begin; si < cls.sweep_end; ++si) {
+                    if (!early[si - cls.sweep_begin]) continue;
+                    const int64_t per = p->h.sweeps[si].n_tiles / pipe->chunks;  // the top qubits of the tile number select the piece
+                    QFE_TRY(launch(si, per * c, per * (c + 1)));
+                }
+            }
         }
+        for (int si = cls.sweep_begin; si < cls.sweep_end; ++si)
+            if (mine(si) && !early[si - cls.sweep_begin]) QFE_TRY(launch(si, 0, p->h.sweeps[si].n_tiles));
         QFE_TRY(reduce_to_vals(ctx, ctx->partials.as<double2>(), (int)n_vals, (int)row, d_vals));
     } else {
         DirectArgs a;
@@ -1296,19 +1338,79 @@ int qfe_expectation(qfe_ctx* ctx, const qfe_plan* p, const void* psi, int dtype,
     return qfe_expectation_class(ctx, p, 0, psi, psi, dtype, out);
 }
 
+namespace {
+struct HostCopy {
+    qfe_ctx* ctx;
+    const char* src;
+    char* dst;
+    size_t piece;
+    std::vector<cudaEvent_t>* ready;
+};
+int issue_piece(void* cookie, int c) {
+    HostCopy* h = static_cast<HostCopy*>(cookie);
+    // modest copies: the source may be pageable, and a piece must not wait behind the whole state
+    const size_t sub = size_t(1) << 28;
+    for (size_t off = 0; off < h->piece; off += sub) {
+        const size_t nb = std::min(sub, h->piece - off);
+        QFE_CUDA(cudaMemcpyAsync(h->dst + c * h->piece + off, h->src + c * h->piece + off, nb, cudaMemcpyHostToDevice, h->ctx->copy_stream));
+    }
+    QFE_CUDA(cudaEventRecord((*h->ready)[c], h->ctx->copy_stream));
+    return QFE_OK;
+}
+}  // namespace
+
 int qfe_expectation_host(qfe_ctx* ctx, const qfe_plan* p, const void* psi_host, int dtype, double out[2]) {
     QFE_REQUIRE(ctx && p && psi_host && out, QFE_ERR_ARG, "qfe_expectation_host: null argument");
+    QFE_REQUIRE(dtype == QFE_C128 || dtype == QFE_C64, QFE_ERR_ARG, "unknown dtype %d", dtype);
     QFE_REQUIRE(p->h.n_local == p->h.n, QFE_ERR_STATE, "qfe_expectation_host needs an unsharded plan");
+    QFE_REQUIRE(p->h.n_slots == 1, QFE_ERR_STATE, "qfe_expectation_host needs a single-operator term set");
     QFE_CUDA(cudaSetDevice(ctx->device));
     const size_t bytes = (size_t(1) << p->h.n) * (dtype == QFE_C128 ? 16 : 8);
     QFE_TRY(ctx->hostvec.reserve(bytes));
-    // chunked upload: many modest copies instead of one huge one (the source may be pageable)
-    const size_t chunk = size_t(1) << 28;
-    for (size_t off = 0; off < bytes; off += chunk) {
-        const size_t nb = std::min(chunk, bytes - off);
-        QFE_CUDA(cudaMemcpyAsync(ctx->hostvec.as<char>() + off, (const char*)psi_host + off, nb, cudaMemcpyHostToDevice, ctx->stream));
+    // The state is uploaded on a second stream in 16 pieces (selected by its top 4 qubits); the first sweeps whose tiles leave those
+    // qubits alone follow the upload piece by piece, so that most of the copy hides behind them.  QFE_HOST_EARLY = number of such
+    // sweeps (0: plain upload, then all sweeps).
+    static const int early_env = [] {
+        const char* e = getenv("QFE_HOST_EARLY");
+        return e ? atoi(e) : 20;
+    }();
+    const int ci = find_class(p, 0);
+    const bool tiles = p->h.use_tiles && !p->force_direct;
+    const int chunks = 16;
+    if (early_env <= 0 || ci < 0 || !tiles || bytes < (size_t(1) << 30)) {
+        const size_t sub = size_t(1) << 28;
+        for (size_t off = 0; off < bytes; off += sub) {
+            const size_t nb = std::min(sub, bytes - off);
+            QFE_CUDA(cudaMemcpyAsync(ctx->hostvec.as<char>() + off, (const char*)psi_host + off, nb, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        return qfe_expectation(ctx, p, ctx->hostvec.p, dtype, out);
     }
-    return qfe_expectation(ctx, p, ctx->hostvec.p, dtype, out);
+    if (!ctx->copy_stream) QFE_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    while ((int)ctx->copy_events.size() < chunks + 1) {
+        cudaEvent_t e;
+        QFE_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->copy_events.push_back(e);
+    }
+    // the landing buffer may still be read by work queued on the compute stream
+    QFE_CUDA(cudaEventRecord(ctx->copy_events[chunks], ctx->stream));
+    QFE_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_events[chunks], 0));
+    std::vector<cudaEvent_t> ready(ctx->copy_events.begin(), ctx->copy_events.begin() + chunks);
+    HostCopy hc{ctx, (const char*)psi_host, ctx->hostvec.as<char>(), bytes / chunks, &ready};
+    UploadPipe pipe;
+    pipe.chunks = chunks;
+    pipe.max_early = early_env;
+    pipe.ready = ready;
+    pipe.issue_copy = issue_piece;
+    pipe.cookie = &hc;
+    out[0] = out[1] = 0.0;
+    std::vector<double> vals;
+    std::vector<int32_t> slots;
+    QFE_TRY(run_class_reduce(ctx, p, ci, ctx->hostvec.p, ctx->hostvec.p, dtype, 0, 1, vals, slots, &pipe));
+    for (size_t i = 0; i < slots.size(); ++i) {
+        out[0] += vals[2 * i];
+        out[1] += vals[2 * i + 1];
+    }
+    return QFE_OK;
 }
 
 int qfe_apply_class(qfe_ctx* ctx, const qfe_plan* p, int x_hi, const void* ket, void* y, int dtype, int accumulate) {

@@ -459,6 +459,11 @@ int qfe_ctx_destroy(qfe_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->copy_stream) {
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamDestroy(ctx->copy_stream);
+    }
+    for (cudaEvent_t e : ctx->copy_events) cudaEventDestroy(e);
     delete ctx;
     return QFE_OK;
 }

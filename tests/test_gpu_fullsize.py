@@ -114,3 +114,26 @@ def test_config5_pool_gradients_at_26_qubits(eng):
         single = eng.expectation(eng.plan(ops[kk]), psi, bra=phi)  # <H psi|tau_k|psi> with a single-operator plan
         assert abs(g[kk] - 2.0 * single.imag) <= RTOL64 * scale, kk
     assert scale > 1e-3
+
+
+def test_host_upload_pipeline_matches_the_device_path(eng):
+    """qfe_expectation_host at a size where the upload is pipelined (state >= 1 GiB: 16 pieces on a copy stream, the first sweeps run
+    piece by piece behind it): same energy as the device-resident call, and the piecewise launches really happened."""
+    from myqlm_fermion_b200 import workloads
+
+    n = 26
+    hpq, hpqrs = workloads.synthetic_h_integrals(n // 2, seed=1234)
+    plan = eng.plan(eng.terms_from_integrals(hpq, hpqrs, constant=-0.5))
+    del hpqrs
+    psi = eng.random_state(n, seed=7)
+    l0 = eng.launch_count()
+    e_dev = eng.expectation(plan, psi)
+    l1 = eng.launch_count()
+    host = psi.cpu().numpy()
+    e_host = eng.expectation_host(plan, host)
+    l2 = eng.launch_count()
+    assert abs(e_host - e_dev) <= 1e-12 * abs(e_dev), (e_host, e_dev)
+    assert (l2 - l1) >= (l1 - l0) + 15, "no sweep ran piece by piece"
+    host[: 1 << 20] = 0.0  # a second call sees the new host data (no stale landing buffer, no race with the previous call)
+    psi[: 1 << 20] = 0.0
+    assert abs(eng.expectation_host(plan, host) - eng.expectation(plan, psi)) <= 1e-12 * abs(e_dev)
