@@ -80,6 +80,7 @@ struct SweepArgs {
     int pstride;        // BATCH: partials of group g start at g * pstride
     unsigned long long slab_amps;  // APPLY with split > 1: CTA part p writes its partial result at out_vec + p * slab_amps
     unsigned long long tile_begin, n_tiles;  // the launch covers tiles [tile_begin, n_tiles)
+    unsigned long long tile_stride;          // gridDim.x / split, set by the launcher
     unsigned long long ket_xor;
     uint8_t run_pos[PLAN_MAX_RUNS];
     uint8_t run_len[PLAN_MAX_RUNS];
@@ -654,7 +655,7 @@ __global__ void __launch_bounds__(NTH, NT_MAX / NTH) tile_sweep_kernel(const __g
     // (a.split sits in the constant bank; nothing of this is kept in registers across the group loops)
     if (MODE == MODE_APPLY) yout += (size_t)(blockIdx.x % (uint32_t)a.split) * a.slab_amps;
 
-    for (unsigned long long tile_id = a.tile_begin + blockIdx.x / (uint32_t)a.split; tile_id < a.n_tiles; tile_id += gridDim.x / (uint32_t)a.split) {
+    for (unsigned long long tile_id = a.tile_begin + blockIdx.x / (uint32_t)a.split; tile_id < a.n_tiles; tile_id += a.tile_stride) {
         // shard position of the tile: deposit the tile number into the bits outside the tile mask
         uint64_t base = 0;
         {
@@ -688,9 +689,9 @@ __global__ void __launch_bounds__(NTH, NT_MAX / NTH) tile_sweep_kernel(const __g
         }
         __syncthreads();
         // next tile of this CTA -> L2 while this one is processed (two 128 B lines per thread)
-        if (a.prefetch_dist > 0 && tile_id + (unsigned long long)a.prefetch_dist * (gridDim.x / (uint32_t)a.split) < a.n_tiles) {
+        if (a.prefetch_dist > 0 && tile_id + (unsigned long long)a.prefetch_dist * a.tile_stride < a.n_tiles) {
             uint64_t nbase = 0;
-            unsigned long long rest = tile_id + (unsigned long long)a.prefetch_dist * (gridDim.x / (uint32_t)a.split);
+            unsigned long long rest = tile_id + (unsigned long long)a.prefetch_dist * a.tile_stride;
             for (int r = 0; r < a.n_runs; ++r) {
                 const int len = a.run_len[r];
                 nbase |= (rest & ((1ull << len) - 1ull)) << a.run_pos[r];
@@ -970,7 +971,7 @@ static int sweep_grid(const qfe_ctx* ctx, const SweepHost& sw, int split) {
 }
 
 template <typename real_t, bool CPLX, int MODE, int NTH>
-static int launch_tile_n(qfe_ctx* ctx, const SweepArgs& args, int grid) {
+static int launch_tile_n(qfe_ctx* ctx, SweepArgs& args, int grid) {
     auto kern = tile_sweep_kernel<real_t, CPLX, MODE, NTH>;
     constexpr size_t smem = Geo<NTH>::SM_TOTAL;
     static int attr_device = -1;  // once per instantiation (and again if another device's context comes by)
@@ -978,6 +979,7 @@ static int launch_tile_n(qfe_ctx* ctx, const SweepArgs& args, int grid) {
         QFE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_device = ctx->device;
     }
+    args.tile_stride = (unsigned long long)(grid / std::max(args.split, 1));
     kern<<<grid, NTH, smem, ctx->stream>>>(args);
     ctx->launches++;
     QFE_CUDA(cudaGetLastError());
@@ -985,17 +987,17 @@ static int launch_tile_n(qfe_ctx* ctx, const SweepArgs& args, int grid) {
 }
 
 template <typename real_t, bool CPLX, int MODE>
-static int launch_tile(qfe_ctx* ctx, const SweepArgs& args, int grid) {
+static int launch_tile(qfe_ctx* ctx, SweepArgs& args, int grid) {
     return sweep_threads(args.k) == NT_MAX ? launch_tile_n<real_t, CPLX, MODE, NT_MAX>(ctx, args, grid) : launch_tile_n<real_t, CPLX, MODE, NT_MAX / 2>(ctx, args, grid);
 }
 
 template <typename real_t, int MODE>
-static int launch_tile_c(qfe_ctx* ctx, const SweepArgs& args, int grid, bool cplx) {
+static int launch_tile_c(qfe_ctx* ctx, SweepArgs& args, int grid, bool cplx) {
     return cplx ? launch_tile<real_t, true, MODE>(ctx, args, grid) : launch_tile<real_t, false, MODE>(ctx, args, grid);
 }
 
 template <int MODE>
-static int launch_tile_d(qfe_ctx* ctx, const SweepArgs& args, int grid, bool cplx, int dtype) {
+static int launch_tile_d(qfe_ctx* ctx, SweepArgs& args, int grid, bool cplx, int dtype) {
     return dtype == QFE_C128 ? launch_tile_c<double, MODE>(ctx, args, grid, cplx) : launch_tile_c<float, MODE>(ctx, args, grid, cplx);
 }
 
