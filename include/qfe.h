@@ -127,8 +127,13 @@ int qfe_expectation_class(qfe_ctx* ctx, const qfe_plan* p, int x_hi, const void*
 int qfe_expectation_class_part(qfe_ctx* ctx, const qfe_plan* p, int x_hi, const void* bra, const void* ket, int dtype, int part, int n_parts, double* out);
 /* whole-vector convenience (n_local == n): <psi|H|psi> in out[0..1]                            */
 int qfe_expectation(qfe_ctx* ctx, const qfe_plan* p, const void* psi, int dtype, double out[2]);
-/* same through HOST memory: psi_host is uploaded in chunks inside the call (end-to-end path)   */
+/* same through HOST memory (end-to-end path): psi_host is uploaded inside the call, in 16 pieces on a copy stream; the first sweeps
+ * whose tiles do not involve the 4 top qubits run piece by piece behind the upload, which hides most of the copy                  */
 int qfe_expectation_host(qfe_ctx* ctx, const qfe_plan* p, const void* psi_host, int dtype, double out[2]);
+/* sharded form of the same: uploads this process's shard (2^n_local amplitudes) from psi_host into the caller's device buffer
+ * psi_dev with the same pipeline and returns the class x_hi = 0 share of <psi|H|psi> in out[0..1] (0 if no term is local); the other
+ * classes follow with qfe_expectation_class[_part] on psi_dev.  Single-operator term sets only.                                     */
+int qfe_expectation_class0_host(qfe_ctx* ctx, const qfe_plan* p, const void* psi_host, void* psi_dev, int dtype, double out[2]);
 /* y_rows (+)= H_class * ket ; accumulate = 0 overwrites y, 1 adds to it                        */
 int qfe_apply_class(qfe_ctx* ctx, const qfe_plan* p, int x_hi, const void* ket, void* y, int dtype, int accumulate);
 int qfe_apply(qfe_ctx* ctx, const qfe_plan* p, const void* psi, void* y, int dtype);

@@ -53,6 +53,7 @@ SIGNATURES = {
     "qfe_expectation_class_part": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, c_double_p]),
     "qfe_expectation": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, c_double_p]),
     "qfe_expectation_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, c_double_p]),
+    "qfe_expectation_class0_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, c_double_p]),
     "qfe_apply_class": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "qfe_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "qfe_commutator_gradients": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, c_double_p]),

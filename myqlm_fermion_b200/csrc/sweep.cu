@@ -1361,15 +1361,13 @@ int issue_piece(void* cookie, int c) {
 }
 }  // namespace
 
-int qfe_expectation_host(qfe_ctx* ctx, const qfe_plan* p, const void* psi_host, int dtype, double out[2]) {
-    QFE_REQUIRE(ctx && p && psi_host && out, QFE_ERR_ARG, "qfe_expectation_host: null argument");
+int qfe_expectation_class0_host(qfe_ctx* ctx, const qfe_plan* p, const void* psi_host, void* psi_dev, int dtype, double out[2]) {
+    QFE_REQUIRE(ctx && p && psi_host && psi_dev && out, QFE_ERR_ARG, "qfe_expectation_class0_host: null argument");
     QFE_REQUIRE(dtype == QFE_C128 || dtype == QFE_C64, QFE_ERR_ARG, "unknown dtype %d", dtype);
-    QFE_REQUIRE(p->h.n_local == p->h.n, QFE_ERR_STATE, "qfe_expectation_host needs an unsharded plan");
-    QFE_REQUIRE(p->h.n_slots == 1, QFE_ERR_STATE, "qfe_expectation_host needs a single-operator term set");
+    QFE_REQUIRE(p->h.n_slots == 1, QFE_ERR_STATE, "qfe_expectation_class0_host needs a single-operator term set");
     QFE_CUDA(cudaSetDevice(ctx->device));
-    const size_t bytes = (size_t(1) << p->h.n) * (dtype == QFE_C128 ? 16 : 8);
-    QFE_TRY(ctx->hostvec.reserve(bytes));
-    // The state is uploaded on a second stream in 16 pieces (selected by its top 4 qubits); the first sweeps whose tiles leave those
+    const size_t bytes = (size_t(1) << p->h.n_local) * (dtype == QFE_C128 ? 16 : 8);
+    // The shard is uploaded on a second stream in 16 pieces (selected by its top 4 qubits); the first sweeps whose tiles leave those
     // qubits alone follow the upload piece by piece, so that most of the copy hides behind them.  QFE_HOST_EARLY = number of such
     // sweeps (0: plain upload, then all sweeps).
     static const int early_env = [] {
@@ -1379,13 +1377,18 @@ int qfe_expectation_host(qfe_ctx* ctx, const qfe_plan* p, const void* psi_host, 
     const int ci = find_class(p, 0);
     const bool tiles = p->h.use_tiles && !p->force_direct;
     const int chunks = 16;
+    out[0] = out[1] = 0.0;
     if (early_env <= 0 || ci < 0 || !tiles || bytes < (size_t(1) << 30)) {
-        const size_t sub = size_t(1) << 28;
+        const size_t sub = size_t(1) << 28;  // modest copies: the source may be pageable
         for (size_t off = 0; off < bytes; off += sub) {
             const size_t nb = std::min(sub, bytes - off);
-            QFE_CUDA(cudaMemcpyAsync(ctx->hostvec.as<char>() + off, (const char*)psi_host + off, nb, cudaMemcpyHostToDevice, ctx->stream));
+            QFE_CUDA(cudaMemcpyAsync((char*)psi_dev + off, (const char*)psi_host + off, nb, cudaMemcpyHostToDevice, ctx->stream));
         }
-        return qfe_expectation(ctx, p, ctx->hostvec.p, dtype, out);
+        if (ci < 0) {
+            QFE_CUDA(cudaStreamSynchronize(ctx->stream));
+            return QFE_OK;
+        }
+        return qfe_expectation_class(ctx, p, 0, psi_dev, psi_dev, dtype, out);
     }
     if (!ctx->copy_stream) QFE_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     while ((int)ctx->copy_events.size() < chunks + 1) {
@@ -1393,26 +1396,34 @@ int qfe_expectation_host(qfe_ctx* ctx, const qfe_plan* p, const void* psi_host, 
         QFE_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         ctx->copy_events.push_back(e);
     }
-    // the landing buffer may still be read by work queued on the compute stream
+    // the destination may still be read by work queued on the compute stream
     QFE_CUDA(cudaEventRecord(ctx->copy_events[chunks], ctx->stream));
     QFE_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_events[chunks], 0));
     std::vector<cudaEvent_t> ready(ctx->copy_events.begin(), ctx->copy_events.begin() + chunks);
-    HostCopy hc{ctx, (const char*)psi_host, ctx->hostvec.as<char>(), bytes / chunks, &ready};
+    HostCopy hc{ctx, (const char*)psi_host, (char*)psi_dev, bytes / chunks, &ready};
     UploadPipe pipe;
     pipe.chunks = chunks;
     pipe.max_early = early_env;
     pipe.ready = ready;
     pipe.issue_copy = issue_piece;
     pipe.cookie = &hc;
-    out[0] = out[1] = 0.0;
     std::vector<double> vals;
     std::vector<int32_t> slots;
-    QFE_TRY(run_class_reduce(ctx, p, ci, ctx->hostvec.p, ctx->hostvec.p, dtype, 0, 1, vals, slots, &pipe));
+    QFE_TRY(run_class_reduce(ctx, p, ci, psi_dev, psi_dev, dtype, 0, 1, vals, slots, &pipe));
     for (size_t i = 0; i < slots.size(); ++i) {
         out[0] += vals[2 * i];
         out[1] += vals[2 * i + 1];
     }
     return QFE_OK;
+}
+
+int qfe_expectation_host(qfe_ctx* ctx, const qfe_plan* p, const void* psi_host, int dtype, double out[2]) {
+    QFE_REQUIRE(ctx && p && psi_host && out, QFE_ERR_ARG, "qfe_expectation_host: null argument");
+    QFE_REQUIRE(dtype == QFE_C128 || dtype == QFE_C64, QFE_ERR_ARG, "unknown dtype %d", dtype);
+    QFE_REQUIRE(p->h.n_local == p->h.n, QFE_ERR_STATE, "qfe_expectation_host needs an unsharded plan");
+    QFE_CUDA(cudaSetDevice(ctx->device));
+    QFE_TRY(ctx->hostvec.reserve((size_t(1) << p->h.n) * (dtype == QFE_C128 ? 16 : 8)));
+    return qfe_expectation_class0_host(ctx, p, psi_host, ctx->hostvec.p, dtype, out);
 }
 
 int qfe_apply_class(qfe_ctx* ctx, const qfe_plan* p, int x_hi, const void* ket, void* y, int dtype, int accumulate) {

@@ -265,6 +265,19 @@ class Engine:
         return out
 
     # ---- shard-level entry points (one x_hi class at a time; ShardedEngine drives these) ------
+    def expectation_class0_host(self, plan: Plan, shard_host: np.ndarray, shard_dev) -> complex:
+        """Upload this process's shard from HOST memory into ``shard_dev`` and return the class-0 (local) share of <psi|H|psi>; the
+        copy runs on a second stream and hides behind the first sweeps (qfe_expectation_class0_host)."""
+        n_amps = 1 << plan.n_local
+        dt = self._check_state(shard_dev, n_amps)
+        if shard_host.dtype != (np.complex128 if dt == C128 else np.complex64) or shard_host.size != n_amps or not shard_host.flags.c_contiguous:
+            raise ValueError("host shard must be a contiguous vector of 2^n_local amplitudes of the device buffer's dtype")
+        self._sync_torch()
+        out = np.zeros(2, dtype=np.float64)
+        check(self.lib.qfe_expectation_class0_host(self.ctx, plan.handle, C.c_void_p(shard_host.ctypes.data), C.c_void_p(shard_dev.data_ptr()), dt,
+                                                   as_ptr(out, C.c_double)))
+        return complex(out[0], out[1])
+
     def expectation_class(self, plan: Plan, x_hi: int, bra_shard, ket_shard, part: int = 0, n_parts: int = 1):
         """Class x_hi's share of <bra|H|ket>: ``bra_shard`` is this rank's shard of the bra,
         ``ket_shard`` the shard (shard ^ x_hi) of the ket.  ``part`` / ``n_parts``: every n_parts-th sweep of the class only."""

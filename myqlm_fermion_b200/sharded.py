@@ -94,16 +94,28 @@ class ShardedEngine:
         return t.cpu().numpy()
 
     # ---- kernel 2 on shards ----------------------------------------------------------------------
-    def expectation(self, plan, ket_shard, bra_shard=None):
+    def expectation_host(self, plan, shard_host, ket_shard):
+        """<psi|H|psi> with this rank's shard arriving from HOST memory: it is uploaded into ``ket_shard`` behind the sweeps of the
+        local class (Engine.expectation_class0_host); the other classes then run on the device copy as in ``expectation``."""
+        if plan.terms.n_slots != 1:
+            raise ValueError("expectation_host needs a single-operator term set")
+        local = self.backend.expectation_class0_host(plan, shard_host, ket_shard)
+        return self.expectation(plan, ket_shard, _class0=local)
+
+    def expectation(self, plan, ket_shard, bra_shard=None, _class0=None):
         """<bra|H|ket> of the whole register (identical on every rank)."""
         bra = ket_shard if bra_shard is None else bra_shard
         n_slots = plan.terms.n_slots
         acc = np.zeros(n_slots, dtype=np.complex128)
+        if _class0 is not None:
+            acc[0] += _class0  # the local class was evaluated during the upload
         # <psi|H|psi> with every class Hermitian: the shard pairs (r, r^x_hi) and (r^x_hi, r) of a class give conjugate numbers.  The
         # two ranks of a pair split the sweeps of the class between them (each with its own shard as the bra) and count their half
         # twice: every rank does half of the work of every non-local class.
         split = bra_shard is None and n_slots == 1 and getattr(plan, "hermitian", False)
         for x_hi in plan.classes:  # the class list is the same on every rank (it depends on the X masks only)
+            if x_hi == 0 and _class0 is not None:
+                continue
             if x_hi != 0 and split:
                 pivot = (x_hi & -x_hi).bit_length() - 1
                 partner = self.exchange(ket_shard, x_hi)

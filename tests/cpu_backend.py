@@ -73,6 +73,10 @@ class CpuBackend:
         out, _ = self._run(plan, x_hi, bra_shard, ket_shard)
         return complex(out[0]) if plan.terms.n_slots == 1 else out
 
+    def expectation_class0_host(self, plan, shard_host, shard_dev):
+        shard_dev.copy_(torch.from_numpy(shard_host))
+        return self.expectation_class(plan, 0, shard_dev, shard_dev) if 0 in plan.classes else 0.0
+
     def apply_class(self, plan, x_hi, ket_shard, y_shard, accumulate, sync=True):
         _, y = self._run(plan, x_hi, ket_shard, ket_shard)
         y = torch.from_numpy(y).to(y_shard.dtype)

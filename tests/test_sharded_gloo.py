@@ -54,6 +54,9 @@ def _worker(rank, world, port, out_dir):
         want_e = np.vdot(psi, want_phi)
         got_e = se.expectation(plan, shard)
         assert abs(got_e - want_e) <= 1e-11 * abs(want_e), (got_e, want_e)
+        landing = torch.zeros_like(shard)  # end-to-end form: the shard arrives from host memory, the local class runs during the upload
+        got_h = se.expectation_host(plan, psi[lo:hi].copy(), landing)
+        assert abs(got_h - want_e) <= 1e-11 * abs(want_e) and torch.equal(landing, shard)
         got_phi = se.apply(plan, shard)
         assert np.max(np.abs(got_phi.numpy() - want_phi[lo:hi])) <= 1e-11 * np.max(np.abs(want_phi))
         assert se.exchanges > 0 and abs(se.dot(shard, shard) - 1.0) < 1e-12

@@ -32,6 +32,9 @@ for enc in ("jordan-wigner", "bravyi-kitaev"):
     e1 = eng.expectation(plan1, full)
     es = se.expectation(plans, shard)
     assert abs(es - e1) <= 1e-12 * abs(e1), (enc, es, e1)
+    landing = torch.zeros_like(shard)  # end-to-end form: shard from host memory, uploaded behind the sweeps of the local class
+    eh = se.expectation_host(plans, shard.cpu().numpy(), landing)
+    assert abs(eh - e1) <= 1e-12 * abs(e1) and torch.equal(landing, shard), (enc, eh, e1)
     phi1 = eng.apply(plan1, full)
     phis = se.apply(plans, shard)
     err = (phis - phi1[lo:hi]).abs().max().item()
