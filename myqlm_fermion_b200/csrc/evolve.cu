@@ -146,9 +146,12 @@ int qfe_pauli_rotations(qfe_ctx* ctx, int nqbits, int64_t K, const uint64_t* x, 
     const int kmax = std::min(nqbits, EV_MAX_TILE_BITS);
     const uint64_t lowmask = (uint64_t(1) << std::min(3, nqbits)) - 1;
     const size_t elt = dtype == QFE_C128 ? 16 : 8;
-    DevBuf d_rots;
-    QFE_TRY(d_rots.alloc(sizeof(RotRec) * EV_MAX_ROT));
+    // all batches are planned first: one upload of every rotation table, then the passes back to back (no allocation, no
+    // synchronisation between them)
     std::vector<RotRec> recs;
+    recs.reserve((size_t)K);
+    std::vector<EvolveArgs> passes;
+    std::vector<int64_t> pass_first;
     int64_t i = 0;
     while (i < K) {
         // greedy batch: consecutive rotations whose X masks fit kmax positions together with the 3 low bits
@@ -204,7 +207,7 @@ int qfe_pauli_rotations(qfe_ctx* ctx, int nqbits, int64_t K, const uint64_t* x, 
                 }
             }
         }
-        recs.clear();
+        pass_first.push_back((int64_t)recs.size());
         for (int64_t r = i; r < j; ++r) {
             RotRec q;
             memset(&q, 0, sizeof(q));
@@ -224,27 +227,39 @@ int qfe_pauli_rotations(qfe_ctx* ctx, int nqbits, int64_t K, const uint64_t* x, 
             q.kpar = (uint32_t)(kk & 1);
             recs.push_back(q);
         }
-        a.n_rot = (int)recs.size();
-        // the previous batch's kernel must be done with the table before it is overwritten: same stream, ordered
-        QFE_CUDA(cudaMemcpyAsync(d_rots.p, recs.data(), sizeof(RotRec) * recs.size(), cudaMemcpyHostToDevice, ctx->stream));
-        QFE_CUDA(cudaStreamSynchronize(ctx->stream));  // recs is reused by the next batch (pageable source)
-        a.rots = d_rots.as<RotRec>();
+        a.n_rot = (int)(j - i);
+        passes.push_back(a);
+        i = j;
+    }
+    if (passes.empty()) return QFE_OK;
+    QFE_TRY(ctx->rots.reserve(sizeof(RotRec) * recs.size()));
+    QFE_CUDA(cudaMemcpyAsync(ctx->rots.p, recs.data(), sizeof(RotRec) * recs.size(), cudaMemcpyHostToDevice, ctx->stream));
+    static int attr_device[2] = {-1, -1};  // per instantiation: the shared-memory opt-in is set once per device
+    for (size_t b = 0; b < passes.size(); ++b) {
+        EvolveArgs& a = passes[b];
+        a.rots = ctx->rots.as<RotRec>() + pass_first[b];
         const size_t smem = (elt << a.k) + sizeof(RotRec) * EV_MAX_ROT;
+        const size_t smem_max = (elt << EV_MAX_TILE_BITS) + sizeof(RotRec) * EV_MAX_ROT;
         const int grid = (int)std::min<unsigned long long>(a.n_tiles, (unsigned long long)ctx->sm_count);
         if (dtype == QFE_C128) {
             auto kern = rotate_tile_kernel<double>;
-            QFE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (attr_device[0] != ctx->device) {
+                QFE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+                attr_device[0] = ctx->device;
+            }
             kern<<<grid, EV_NT, smem, ctx->stream>>>(a);
         } else {
             auto kern = rotate_tile_kernel<float>;
-            QFE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (attr_device[1] != ctx->device) {
+                QFE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+                attr_device[1] = ctx->device;
+            }
             kern<<<grid, EV_NT, smem, ctx->stream>>>(a);
         }
         ctx->launches++;
         QFE_CUDA(cudaGetLastError());
-        i = j;
     }
-    QFE_CUDA(cudaStreamSynchronize(ctx->stream));  // d_rots is freed on return
+    QFE_CUDA(cudaStreamSynchronize(ctx->stream));  // the call is synchronous: recs (pageable) and the table stay valid until here
     return QFE_OK;
 }
 

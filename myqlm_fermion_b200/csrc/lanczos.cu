@@ -143,12 +143,15 @@ __global__ void __launch_bounds__(VT) fill_random_kernel(typename C2<real_t>::ty
 // one product chain per thread and block) x table: about three complex multiplications per amplitude instead of n, so the
 // kernel runs at the HBM write rate.
 constexpr int PS_LOW_BITS = 11;
+struct ProductFactors {
+    double ab[4 * 64];  // (Re alpha_q, Im alpha_q, Re beta_q, Im beta_q) per qubit: travels as the kernel parameter
+};
 template <typename real_t>
 __global__ void __launch_bounds__(VT) product_state_kernel(typename C2<real_t>::type* __restrict__ x, int n_local, uint64_t shard, int n,
-                                                            const double* __restrict__ ab) {
+                                                            const __grid_constant__ ProductFactors f) {
     __shared__ double s_ab[4 * 64];
     __shared__ double2 s_lo[1 << PS_LOW_BITS];
-    for (int i = threadIdx.x; i < 4 * n; i += VT) s_ab[i] = ab[i];
+    for (int i = threadIdx.x; i < 4 * n; i += VT) s_ab[i] = f.ab[i];
     __syncthreads();
     const int L = n_local < PS_LOW_BITS ? n_local : PS_LOW_BITS;
     const int n_lo = 1 << L;
@@ -362,14 +365,14 @@ int qfe_vec_fill_random(qfe_ctx* ctx, void* x, int64_t n, int dtype, uint64_t se
 int qfe_vec_product_state(qfe_ctx* ctx, void* x, int n_local, int shard, int n, const double* alpha_beta, int dtype) {
     QFE_REQUIRE(ctx && x && alpha_beta && n >= 1 && n <= 64 && n_local >= 0 && n_local <= n, QFE_ERR_ARG, "qfe_vec_product_state: bad argument");
     QFE_CUDA(cudaSetDevice(ctx->device));
-    DevBuf d_ab;
-    QFE_TRY(d_ab.alloc(sizeof(double) * 4 * n));
-    QFE_CUDA(cudaMemcpyAsync(d_ab.p, alpha_beta, sizeof(double) * 4 * n, cudaMemcpyHostToDevice, ctx->stream));
+    ProductFactors f;
+    memset(&f, 0, sizeof(f));
+    memcpy(f.ab, alpha_beta, sizeof(double) * 4 * n);
     const int64_t n_amps = int64_t(1) << n_local;
     if (dtype == QFE_C128)
-        product_state_kernel<double><<<vec_grid(ctx, n_amps), VT, 0, ctx->stream>>>((double2*)x, n_local, (uint64_t)shard, n, d_ab.as<double>());
+        product_state_kernel<double><<<vec_grid(ctx, n_amps), VT, 0, ctx->stream>>>((double2*)x, n_local, (uint64_t)shard, n, f);
     else
-        product_state_kernel<float><<<vec_grid(ctx, n_amps), VT, 0, ctx->stream>>>((float2*)x, n_local, (uint64_t)shard, n, d_ab.as<double>());
+        product_state_kernel<float><<<vec_grid(ctx, n_amps), VT, 0, ctx->stream>>>((float2*)x, n_local, (uint64_t)shard, n, f);
     ctx->launches++;
     QFE_CUDA(cudaGetLastError());
     QFE_CUDA(cudaStreamSynchronize(ctx->stream));
