@@ -14,6 +14,10 @@
 using cplx = std::complex<double>;
 using namespace qfe;
 
+static int emul_split = 1;
+// number of slices every range is walked in (the kernel's split of small shards); 1 = off
+extern "C" void plan_emul_set_split(int split) { emul_split = split < 1 ? 1 : split; }
+
 extern "C" int plan_emul_run(int n, int64_t T, const uint64_t* x, const uint64_t* z, const double* c, const int32_t* owner, int64_t n_slots,
                              const double* constant, int n_local, int shard, int tile_bits, int max_terms, int max_groups, int x_hi,
                              const double* bra_, const double* ket_, double* out_slots, double* y_, int64_t* stats /* sweeps, groups, terms, classes */,
@@ -105,8 +109,16 @@ extern "C" int plan_emul_run(int n, int64_t T, const uint64_t* x, const uint64_t
                         if (g0 != g_expect || (int64_t)(d1 & 0xffffu) != t_expect || g1 <= g0) return 10;  // ranges tile the sweep's groups in order
                         if (skipbit && (skipbit < (uint32_t)PLAN_U_SHIFT || skipbit >= (uint32_t)s.k || s.ket_xor != 0)) return 11;
                         if (kind != KIND_FAST && kind != KIND_RUNS && kind != (KIND_RUNS | KIND_XROW)) return 12;
-                        int64_t tb = s.term_begin + t_expect;
-                        for (int gl = g0; gl < g1; ++gl) {
+                        // the groups of a range in `emul_split` slices, each entered through the second header word of its first
+                        // group, exactly as the CTAs that share a tile of a small shard do (emul_split = 1: the whole range)
+                        int64_t tb_end = s.term_begin + t_expect;
+                        for (int part = 0; part < emul_split; ++part) {
+                        const int gs = g0 + (int)((uint32_t)(g1 - g0) * (uint32_t)part / (uint32_t)emul_split);
+                        const int ge = g0 + (int)((uint32_t)(g1 - g0) * (uint32_t)(part + 1) / (uint32_t)emul_split);
+                        if (gs == ge) continue;
+                        int64_t tb = emul_split > 1 ? s.term_begin + (int64_t)p.g_hdr[2 * (s.group_begin + gs) + 1] : tb_end;
+                        if (tb != tb_end) return 29;  // slices follow each other in the staged terms
+                        for (int gl = gs; gl < ge; ++gl) {
                             const int g = s.group_begin + gl;
                             const uint32_t ha = p.g_hdr[2 * g];
                             const uint32_t xl = ha & HDR_XL_MASK;
@@ -147,8 +159,10 @@ extern "C" int plan_emul_run(int n, int64_t T, const uint64_t* x, const uint64_t
                                 out[p.g_slot[g]] += std::conj(bra[row]) * contrib;
                             }
                         }
+                        tb_end = tb;
+                        }
                         g_expect = g1;
-                        t_expect = tb - s.term_begin;
+                        t_expect = tb_end - s.term_begin;
                     }
                     if (g_expect != s.group_end - s.group_begin || s.term_begin + t_expect != s.term_end) return 8;
                     y[row] += acc_row;

@@ -79,6 +79,23 @@ def test_unsharded_plan_reproduces_apply_and_expectation(emul, enc, tile_bits):
     assert 1 <= stats[0] <= n_groups
 
 
+@pytest.mark.parametrize("split", [2, 3, 16])
+def test_ranges_walked_in_slices_like_the_ctas_of_a_small_shard(emul, split):
+    """Shards with fewer tiles than SMs: several CTAs stage the same tile and each walks a slice of the groups of every range, entering
+    the staged terms through the second header word of the slice's first group.  The interpreter walks the slices the same way."""
+    n = 12
+    x, z, c, k = _molecule(6, "jordan-wigner", constant=-0.2)
+    psi = _state(n, 3)
+    want_phi = spin.apply_packed(n, x, z, c, k, psi)
+    emul.plan_emul_set_split(split)
+    try:
+        out, y, _ = _run(emul, n, x, z, c, np.zeros(len(x)), 1, [k], n, 0, 10, 0, psi, psi, half_visit=1)
+    finally:
+        emul.plan_emul_set_split(1)
+    assert np.max(np.abs(y - want_phi)) <= 1e-12 * np.max(np.abs(want_phi))
+    assert abs(out[0] - np.vdot(psi, want_phi).real) <= 1e-12 * abs(np.vdot(psi, want_phi))
+
+
 @pytest.mark.parametrize("n_local", [9, 10])
 def test_sharded_classes_recombine(emul, n_local):
     n = 12
