@@ -13,7 +13,12 @@
 //     the part outside the tile is a second mask against the tile number (real-coefficient sweeps keep their term records in the
 //     kernel parameter = constant bank, next to the shared-memory pipe) or folded into the staged coefficient per tile;
 //   * W_x(b) = sum_t c_t (-1)^{|z_t & b|} costs one integer multiply-add on the sign bit and one DADD per (term, thread);
-//   * the expectation is reduced by warp shuffles, then per block, then by a fixed-order reduce kernel (bit-reproducible).
+//   * the expectation is reduced by warp shuffles, then per block, then by ONE fixed-order reduce kernel per class (bit-reproducible);
+//   * APPLY accumulates W_x(row) * partner in registers and leaves through the tile: y is read and written in the natural order the
+//     tile was staged in (128 B contiguous, 8 loads in flight per thread, its lines prefetched to L2 before the group loops);
+//   * a shard with fewer tiles than SMs is worked on by up to 16 CTAs per tile, each with a slice of the groups of every range;
+//   * qfe_expectation_host / qfe_expectation_class0_host upload the state on a second stream in 16 pieces and run the first sweeps
+//     piece by piece behind the copy.
 // No tensor cores: this is an XOR-gather with +-1 weights, not a dense contraction.
 #include <algorithm>
 #include <cstdlib>
