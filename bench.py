@@ -7,8 +7,13 @@ Jordan-Wigner Hamiltonian (BASELINE.json config 4 family) in terms*amps/s.
 
 One "step" = one evaluation of <psi|H|psi> over the whole (sharded) statevector.
 N=1: 32 qubits (random 8-fold-symmetric integrals on 32 spin-orbitals, 94 848 Pauli terms, complex128,
-68.7 GB state).  N=2/4/8: 33/34/34 qubits, state sharded by its high qubits, one process per GPU
-(torchrun), NCCL send/recv per x_hi class.  Prints ONE JSON line on rank 0.
+68.7 GB state).  N=2/4/8: 32/33/34 qubits (a 2^31-amplitude shard = 34.4 GB per GPU), state sharded by its
+high qubits, one process per GPU (torchrun), NCCL send/recv per x_hi class.  Prints ONE JSON line on rank 0.
+
+Order of a run (sized so that the driver's --steps 20 --warmup 5 ends inside its per-N limit): the W warm-up
+steps come first and the end-to-end leg lives inside them -- one warm-up through the HOST-buffer call, then up
+to two timed ones (`e2e`), the rest device-resident -- then the K timed device-resident steps (`value`).  After
+the first step a projected wall time goes to stderr.
 """
 
 from __future__ import annotations
@@ -34,8 +39,21 @@ BYTES_PER_SWEEP_AMP = {"c128": 16, "c64": 8}  # every amplitude 
 
 
 def qubits_for(n_gpus: int) -> int:
-    # BASELINE.json: 32 qubits on 1 B200 ... 34 qubits on 8 B200
-    return {1: 32, 2: 33, 4: 34, 8: 34}.get(n_gpus, 32)
+    # BASELINE.json: 32 qubits on 1 B200 ... 34 qubits on 8 B200; 2 and 4 GPUs keep the 8-GPU shard (2^31 amplitudes per GPU)
+    return {1: 32, 2: 32, 4: 33, 8: 34}.get(n_gpus, 32)
+
+
+def ncu_traffic(n_local: int, dtype: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the ncu --set full capture recorded in
+    profiles/ncu_traffic.json (written by tools/ncu_summary.py from the .ncu-rep of the round); None where no capture exists."""
+    p = ROOT / "profiles" / "ncu_traffic.json"
+    try:
+        for row in json.loads(p.read_text())["captures"]:
+            if row["n_local"] == n_local and row["dtype"] == dtype:
+                return float(row["dram_bytes_read"]) + float(row["dram_bytes_write"])
+    except Exception:
+        pass
+    return None
 
 
 def measured_peak():
@@ -103,6 +121,10 @@ class ClockSampler:
 # reference arm: the reference's CPU algorithm (oracle port), bounded sample, all host cores
 # ------------------------------------------------------------------------------------------------
 def cpu_sample(n: int, workers: int, steps: int, warmup: int):
+    """The reference's CPU algorithm on an n-qubit member of the bench generator: get_matrix(sparse=True) ONCE (build_s), then
+    `steps` evaluations vdot(psi, H psi) on the cached matrix (eval_s each).  Two rates come back: `value_cached` counts the
+    evaluations only (what a VQE loop on the reference pays per energy once the matrix exists) and `value_rebuild` charges every
+    evaluation with a build (SpinHamiltonian.get_matrix recomputes the matrix on every call, hamiltonians.py:163-211)."""
     from concurrent.futures import ProcessPoolExecutor
 
     from oracle import baseline
@@ -113,17 +135,37 @@ def cpu_sample(n: int, workers: int, steps: int, warmup: int):
     psi /= np.linalg.norm(psi)
     pool = ProcessPoolExecutor(workers) if workers > 1 else None
     try:
-        for _ in range(warmup):
-            baseline.reference_energy(n, triples, const, psi, workers, pool)
         t0 = time.perf_counter()
-        for _ in range(steps):
-            e, _, _ = baseline.reference_energy(n, triples, const, psi, workers, pool)
-        dt = time.perf_counter() - t0
+        mat = baseline.reference_matrix(n, triples, const, workers, pool)
+        build_s = time.perf_counter() - t0
     finally:
         if pool is not None:
             pool.shutdown()
+    for _ in range(warmup):
+        np.vdot(psi, mat.dot(psi))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        e = np.vdot(psi, mat.dot(psi))
+    eval_s = (time.perf_counter() - t0) / steps
     T = len(triples)
-    return {"T": T, "n": n, "seconds_per_step": dt / steps, "value": T * float(1 << n) * steps / dt, "energy": e.real}
+    work = T * float(1 << n)
+    return {"T": T, "n": n, "build_s": build_s, "eval_s": eval_s, "value_cached": work / eval_s, "value_rebuild": work / (build_s + eval_s),
+            "energy": float(np.real(e)), "nnz": int(mat.nnz)}
+
+
+def cpu_baseline_dict(r, cores):
+    return {
+        "value": r["value_cached"], "unit": UNIT, "cores": cores, "kind": "port",
+        "sample": f"{r['n']}-qubit member of the same generator ({r['T']} Pauli terms, nnz {r['nnz']}): oracle port of get_matrix(sparse=True) built once "
+                  f"(term list split over {cores} processes), then vdot(psi, H psi) per step on the cached CSR matrix",
+        "build_s": r["build_s"], "eval_s": r["eval_s"], "value_cached_matrix": r["value_cached"], "value_rebuild_per_step": r["value_rebuild"],
+        "note": "value = evaluations on the cached matrix only (the favourable reading for the CPU path); value_rebuild_per_step charges "
+                "every evaluation with a get_matrix() build, which is what calling SpinHamiltonian.get_matrix per energy costs",
+    }
+
+
+def cpu_sample_qubits(cores: int) -> int:
+    return 14 if cores >= 8 else 12
 
 
 def run_reference(args):
@@ -133,15 +175,17 @@ def run_reference(args):
     from oracle import baseline
 
     cores = baseline.usable_cores()
-    n = 14 if cores >= 8 else 12
-    r = cpu_sample(n, cores, max(1, args.steps), max(0, min(args.warmup, 1)))
-    sample = f"{n}-qubit member of the same generator ({r['T']} Pauli terms): get_matrix(sparse=True) kron chain + vdot per step, term list split over {cores} processes"
+    n = cpu_sample_qubits(cores)
+    r = cpu_sample(n, cores, max(1, args.steps), max(0, args.warmup))
+    cfg = bench_config(args.gpus, qubits_for(args.gpus), None, None)
+    cfg["workload"] += f"; THIS ARM RAN A BOUNDED SAMPLE: the {n}-qubit member of the same generator ({r['T']} Pauli terms) on {cores} host cores"
+    cfg["sample_n_qubits"] = n
+    cfg["sample_pauli_terms"] = r["T"]
     line = {
-        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * r["seconds_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c128",
-        "data": "synthetic", "config": bench_config(args.gpus, qubits_for(args.gpus), None, None),
-        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": METRIC, "value": r["value_cached"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * r["eval_s"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c128",
+        "data": "synthetic", "config": cfg, "cpu_baseline": cpu_baseline_dict(r, cores),
+        "e2e": {"value": r["value_cached"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
@@ -149,7 +193,8 @@ def run_reference(args):
 
 def bench_config(n_gpus, n, T, plan):
     cfg = {
-        "workload": f"config4 family: random 8-fold-symmetric integrals on {n} spin-orbitals (seed 1234), Jordan-Wigner, <psi|H|psi> on a random complex state",
+        "workload": f"config4 family: random 8-fold-symmetric integrals on {n} spin-orbitals (seed 1234), Jordan-Wigner, <psi|H|psi> on a random complex state"
+        + ("" if n_gpus == 1 else f"; {n} qubits on {n_gpus} GPUs = one 2^{n - (n_gpus.bit_length() - 1)}-amplitude complex128 shard per GPU"),
         "n_qubits": n, "n_gpus": n_gpus, "sharding": f"statevector split by its {max(n_gpus.bit_length() - 1, 0)} high qubits, one process per GPU",
         "l2": "inputs larger than L2 (each sweep streams the whole shard, >= 34 GB)",
     }
@@ -162,6 +207,7 @@ def bench_config(n_gpus, n, T, plan):
 
 # ------------------------------------------------------------------------------------------------
 def main():
+    t_proc0 = time.perf_counter()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2)
@@ -233,6 +279,7 @@ def main():
         step = lambda: eng.expectation(plan, psi)
     n_local = plan.n_local
     shard_bytes = (1 << n_local) * elt
+    amps_f = float(1 << n)
 
     def barrier():
         torch.cuda.synchronize()
@@ -260,29 +307,107 @@ def main():
             ms, launches = float(tmax[0]), int(t[1])
         return ms, launches, val
 
-    for _ in range(args.warmup):
+    t_start = time.perf_counter()
+
+    # ---- end-to-end leg preparation: every rank stages its shard in pinned HOST memory ----
+    e2e_skip = None
+    host_np = None
+    pinned = False
+    if not args.no_e2e:
+        try:
+            import psutil
+
+            avail = psutil.virtual_memory().available
+        except Exception:
+            avail = None
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+        ok = not (avail is not None and avail < 1.15 * shard_bytes * local_world)
+        if world > 1:  # one decision for all ranks: the end-to-end leg contains collectives
+            flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            ok = bool(flag.item())
+        if not ok:
+            avail = avail or 0
+            e2e_skip = f"host memory: {avail / 2**30:.0f} GiB available, {shard_bytes * local_world / 2**30:.0f} GiB needed for the shards of {local_world} ranks"
+        else:
+            pinned = True
+            try:
+                host = torch.empty(1 << n_local, dtype=tdtype, pin_memory=True)
+            except RuntimeError:
+                host = torch.empty(1 << n_local, dtype=tdtype)
+                pinned = False
+            host.copy_(psi)
+            torch.cuda.synchronize()
+            host_np = host.numpy()
+    if host_np is not None:
+        if world == 1:
+            # the user-facing call uploads into a landing buffer of the library; when the device cannot hold a second state the sharded
+            # form of the same call uploads into the caller's buffer instead (same pipeline, same kernels)
+            free_b = torch.cuda.mem_get_info(dev)[0]
+            if free_b > shard_bytes + (4 << 30):
+                e2e_call, e2e_step = "qfe_expectation_host", (lambda: eng.expectation_host(plan, host_np))
+            else:
+                e2e_call, e2e_step = "qfe_expectation_class0_host", (lambda: eng.expectation_class0_host(plan, host_np, psi))
+        else:
+            e2e_call = "qfe_expectation_class0_host + qfe_expectation_class_part per x_hi class"
+
+            def e2e_step():  # the shard is uploaded into psi inside the library call, behind the sweeps of the local class
+                return se.expectation_host(plan, host_np, psi)
+
+    # ---- warm-up (W steps); the end-to-end leg is part of it: 1 untimed + up to 2 timed steps through the host-buffer call ----
+    def project(first_step_s, what):
+        if rank == 0:
+            total = (time.perf_counter() - t_proc0) + first_step_s * (args.warmup + args.steps - 1) + 20.0
+            print(f"[bench] first {what} step {first_step_s:.1f} s -> projected wall time of this run ~{total:.0f} s "
+                  f"({args.warmup} warm-up + {args.steps} timed steps)", file=sys.stderr, flush=True)
+
+    e2e = None
+    warm_left = args.warmup
+    first_timed = False
+    if host_np is not None:
+        e2e_warm = 1 if args.warmup >= 2 else 0
+        e2e_timed = max(1, min(2, args.warmup - e2e_warm))
+        if e2e_warm:
+            t0 = time.perf_counter()
+            e2e_step()
+            torch.cuda.synchronize()
+            project(time.perf_counter() - t0, "end-to-end")
+            first_timed = True
+        ms2, _, energy2 = timed(e2e_step, e2e_timed)
+        warm_left = max(0, args.warmup - e2e_warm - e2e_timed)
+        e2e = {
+            "value": T * amps_f * e2e_timed / (ms2 / 1e3), "unit": UNIT, "h2d_bytes_per_step": shard_bytes * world, "d2h_bytes_per_step": 16 * world,
+            "steps": e2e_timed, "ms_per_step": ms2 / e2e_timed, "host_memory": "pinned" if pinned else "pageable", "call": e2e_call,
+            "note": "timed inside the warm-up phase, after one untimed step through the same call",
+        }
+    for i in range(warm_left):
+        t0 = time.perf_counter()
         step()
+        if not first_timed:
+            torch.cuda.synchronize()
+            project(time.perf_counter() - t0, "device-resident")
+            first_timed = True
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     ms, launches, energy = timed(step, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     sec = ms / 1e3
-    amps = float(1 << n)
-    value = T * amps * args.steps / sec
+    value = T * amps_f * args.steps / sec
+    if e2e is not None:
+        e2e["energy_matches_device"] = bool(abs(energy2 - energy) <= 1e-10 * abs(energy))
 
-    # ---- roofline of the dominant kernel (tile_sweep_kernel): HBM, 16 B (c128) per amplitude per sweep ----
+    # ---- roofline of the dominant kernel (EXPECT sweep): HBM, 16 B (c128) per amplitude per sweep ----
     peak, peak_src = measured_peak()
     sweeps_per_step = plan.n_sweeps  # per rank; every rank launches the same number of sweeps over its own shard
     sweep_launches = sweeps_per_step * args.steps
     avg_launch_s = sec / max(sweep_launches, 1)  # upper bound: includes the (tiny) reduce kernels and, for N>1, the exchanges
     achieved = shard_bytes / avg_launch_s / 1e9
-    # DRAM bytes of one sweep launch from the ncu --set full capture under profiles/ (dram__bytes_read.sum + dram__bytes_write.sum;
-    # r01_sweep_v6_32q_ncu.txt: 68.742878 GB + 8.92 MB for a 2^32-amplitude complex128 shard); None where no capture exists
-    ncu_traffic = {(32, "c128"): 68.742878e9 + 8.920320e6}.get((n_local, args.dtype))
     roofline = {
-        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic,
-        "kernel": "tile_sweep_kernel<EXPECT>", "peak_source": peak_src, "bytes_per_launch": shard_bytes, "avg_launch_ms": 1e3 * avg_launch_s,
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(n_local, args.dtype),
+        "kernel": "tile_expect_async_kernel (real-coefficient EXPECT sweeps; tile_sweep_kernel<EXPECT> for the others)", "peak_source": peak_src,
+        "bytes_per_launch": shard_bytes, "avg_launch_ms": 1e3 * avg_launch_s,
         "terms_per_sweep": T / max(sweeps_per_step, 1),
         "note": "each sweep evaluates terms_per_sweep Pauli terms per amplitude from one HBM pass, so the kernel is issue/shared-memory bound by design; "
         "equiv_gbs_one_sweep_per_xmask is the HBM rate a one-pass-per-X-mask schedule would need for the same throughput",
@@ -302,52 +427,6 @@ def main():
         "note": "algorithmic shared-memory bytes (partner rows + tile staging) / time; peak = 128 B/clk/SM x SMs x sampled SM clock",
     }
 
-    # ---- e2e: the same step through the C-ABI call with HOST buffers (pinned), H2D inside the timed region ----
-    e2e = None
-    e2e_skip = None
-    if not args.no_e2e:
-        # every rank stages its shard in host memory: make sure the box has room for all of them before pinning
-        try:
-            import psutil
-
-            avail = psutil.virtual_memory().available
-        except Exception:
-            avail = None
-        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
-        ok = not (avail is not None and avail < 1.15 * shard_bytes * local_world)
-        if world > 1:  # one decision for all ranks: the end-to-end leg contains collectives
-            flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-            ok = bool(flag.item())
-        if not ok:
-            avail = avail or 0
-            e2e_skip = f"host memory: {avail / 2**30:.0f} GiB available, {shard_bytes * local_world / 2**30:.0f} GiB needed for the shards of {local_world} ranks"
-    if not args.no_e2e and e2e_skip is None:
-        pinned = True
-        try:
-            host = torch.empty(1 << n_local, dtype=tdtype, pin_memory=True)
-        except RuntimeError:
-            host = torch.empty(1 << n_local, dtype=tdtype)
-            pinned = False
-        host.copy_(psi)
-        torch.cuda.synchronize()
-        host_np = host.numpy()
-        if world == 1:
-            del psi
-            torch.cuda.empty_cache()
-            e2e_step = lambda: eng.expectation_host(plan, host_np)
-        else:
-            def e2e_step():  # the shard is uploaded into psi inside the library call, behind the sweeps of the local class
-                return se.expectation_host(plan, host_np, psi)
-        e2e_step()  # warm-up (allocates the landing buffer)
-        e2e_steps = max(1, min(args.steps, 2))
-        ms2, _, energy2 = timed(e2e_step, e2e_steps)
-        e2e = {
-            "value": T * amps * e2e_steps / (ms2 / 1e3), "unit": UNIT, "h2d_bytes_per_step": shard_bytes * world, "d2h_bytes_per_step": 16 * world,
-            "steps": e2e_steps, "ms_per_step": ms2 / e2e_steps, "energy_matches_device": bool(abs(energy2 - energy) <= 1e-10 * abs(energy)),
-            "host_memory": "pinned" if pinned else "pageable",
-        }
-
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -355,11 +434,10 @@ def main():
 
     cpu = None
     if not args.no_cpu and world == 1:
-        r = cpu_sample(13, 1, 1, 0)
-        cpu = {
-            "value": r["value"], "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"13-qubit member of the same generator ({r['T']} Pauli terms): oracle port of get_matrix(sparse=True) + vdot, one evaluation, {r['seconds_per_step']:.1f} s",
-        }
+        from oracle import baseline
+
+        cores = baseline.usable_cores()
+        cpu = cpu_baseline_dict(cpu_sample(cpu_sample_qubits(cores), cores, 20, 2), cores)  # the reference arm's sample, on the same host cores
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -371,7 +449,7 @@ def main():
     if e2e_skip is not None:
         line["e2e_skipped"] = e2e_skip
     if se is not None:
-        line["exchanges_per_step"] = se.exchanges // max(args.warmup + args.steps + (0 if e2e is None else 1 + e2e["steps"]), 1)
+        line["exchanges_per_step"] = se.exchanges // max(args.warmup + args.steps, 1)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

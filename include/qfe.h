@@ -143,6 +143,11 @@ int qfe_apply(qfe_ctx* ctx, const qfe_plan* p, const void* psi, void* y, int dty
 int qfe_commutator_gradients(qfe_ctx* ctx, const qfe_plan* h_plan, const qfe_plan* pool_plan,
                              const void* psi, void* scratch, int dtype, double* grads);
 
+/* Development aid, not part of the reference-facing surface: with QFE_PROF=1 in the environment the sweep kernels count, per warp of a
+ * CTA (16) and phase of the tile loop (8 slots: wait for the tile, issue/own rows, group loops, barrier skew, loads), the cycles spent;
+ * cycles = 16*8 values summed over the CTAs and launches since the last reset.  All zero without QFE_PROF.                         */
+int qfe_dev_phase_cycles(qfe_ctx* ctx, uint64_t* cycles, int reset);
+
 /* ---- kernel 3: Lanczos ground state on the matrix-free apply ------------------------------ */
 /* Replaces eigvalsh / eigsh(get_matrix(sparse=True), which="SA") at the reference's call sites
  * (tests/integration/test_integration_models.py:102-103, test_integration_adaptvqe.py:97).

@@ -57,6 +57,7 @@ SIGNATURES = {
     "qfe_apply_class": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "qfe_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "qfe_commutator_gradients": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, c_double_p]),
+    "qfe_dev_phase_cycles": (C.c_int, [C.c_void_p, c_u64_p, C.c_int]),
     "qfe_lanczos": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int, c_double_p, c_int_p, c_double_p]),
     "qfe_vec_dot": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, c_double_p]),
     "qfe_vec_axpy": (C.c_int, [C.c_void_p, c_double_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]),

@@ -83,6 +83,7 @@ struct qfe_ctx {
     cudaStream_t copy_stream = nullptr;      // upload stream of qfe_expectation_host
     std::vector<cudaEvent_t> copy_events;
     qfe::DevBuf rots;       // rotation tables of qfe_pauli_rotations (all batches of one call)
+    qfe::DevBuf prof;       // development: phase cycle counters of the sweep kernels (QFE_PROF=1)
     qfe::DevBuf slabs;      // per-part partial results of APPLY sweeps whose tiles are shared by several CTAs (small shards)
     void* pinned = nullptr; // small pinned host buffer for scalar read-back
     size_t pinned_bytes = 0;

@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -414,17 +415,46 @@ int build_plan(const TermView& t, int n_local, int shard, const PlanLimits& lim,
                     }
                     gi.skipbit = 0;
                     gi.pol = 0;
-                    if (hermitian && !cplx && !gi.imag && kxor == 0 && (gi.xl >> PLAN_U_SHIFT) != 0) {
-                        gi.skipbit = 31 - __builtin_clz(gi.xl);
-                        // the rows with skip bit == pol do the work of this group: keep the two halves of every bit level equal
-                        const double cost = 48.0 + 6.0 * g.nt;
-                        gi.pol = pol_load[gi.skipbit][1] < pol_load[gi.skipbit][0] ? 1 : 0;
-                        pol_load[gi.skipbit][gi.pol] += cost;
-                    }
+                    if (hermitian && !cplx && !gi.imag && kxor == 0 && (gi.xl >> PLAN_U_SHIFT) != 0) gi.skipbit = 31 - __builtin_clz(gi.xl);
                     for (int64_t i = g.tb; i < g.tb + g.nt; ++i) gi.order.push_back(i);
                     const bool xrow = (gi.xl & regmask) != 0;
                     gi.kind = (fast && !xrow) ? KIND_FAST : (KIND_RUNS | (xrow ? KIND_XROW : 0));
                     if (!fast) std::stable_sort(gi.order.begin(), gi.order.end(), [&](int64_t p, int64_t q) { return zreg_of(p) < zreg_of(q); });
+                }
+                // Polarity of the half-visited groups: the rows whose skip bit equals `pol` do the work of a group, the others skip it.  Every
+                // warp waits for the slowest one at the end of a tile, so the two halves of every skip-bit level must carry equal work:
+                // longest-processing-time order (heaviest group first, each to the lighter half) on a cost model of one group visit
+                // (QFE_PLAN_COST=base,per_term,per_run; QFE_PLAN_BALANCE=0: assignment in group order, the round-1 behaviour).
+                {
+                    static const int balance = [] {
+                        const char* e = getenv("QFE_PLAN_BALANCE");
+                        return e ? atoi(e) : 1;
+                    }();
+                    static double cost_w[3] = {48.0, 6.0, 0.0};
+                    static const bool cost_init = [] {
+                        const char* e = getenv("QFE_PLAN_COST");
+                        if (e) sscanf(e, "%lf,%lf,%lf", &cost_w[0], &cost_w[1], &cost_w[2]);
+                        return true;
+                    }();
+                    (void)cost_init;
+                    std::vector<std::pair<double, size_t>> half;  // (cost, index into info)
+                    for (size_t a = 0; a < info.size(); ++a) {
+                        if (info[a].skipbit == 0) continue;
+                        const Group& g = groups[info[a].gi];
+                        int runs = 0;
+                        if (info[a].kind != KIND_FAST) {
+                            uint32_t seen = 0;
+                            for (int64_t i = g.tb; i < g.tb + g.nt; ++i) seen |= 1u << zreg_of(i);
+                            runs = __builtin_popcount(seen);
+                        }
+                        half.push_back({cost_w[0] + cost_w[1] * g.nt + cost_w[2] * runs, a});
+                    }
+                    if (balance) std::stable_sort(half.begin(), half.end(), [](const std::pair<double, size_t>& p, const std::pair<double, size_t>& q) { return p.first > q.first; });
+                    for (const auto& h : half) {
+                        GInfo& gi = info[h.second];
+                        gi.pol = pol_load[gi.skipbit][1] < pol_load[gi.skipbit][0] ? 1 : 0;
+                        pol_load[gi.skipbit][gi.pol] += h.first;
+                    }
                 }
                 std::vector<size_t> ord(take.size());
                 for (size_t a = 0; a < ord.size(); ++a) ord[a] = a;

@@ -22,6 +22,7 @@
 // No tensor cores: this is an XOR-gather with +-1 weights, not a dense contraction.
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 #include "plan_host.h"
@@ -62,6 +63,7 @@ template <> struct __align__(16) TermRec<float, true> { float c; float ci; uint3
 // (double, or float in c_lo for complex64 states), the word t_zl and the packed outer z bits t_zoc of plan_host.h
 struct TermConst { uint32_t c_lo, c_hi, zp, zoc; };
 constexpr int SWEEP_CONST_TERMS = 1920;  // 30 KB of the 32 KB a kernel may take as parameters
+constexpr int PROF_PHASES = 8;           // development counters: per warp, cycles spent in each phase of the tile loop
 
 struct SweepArgs {
     const void* ket;
@@ -87,10 +89,14 @@ struct SweepArgs {
     unsigned long long tile_begin, n_tiles;  // the launch covers tiles [tile_begin, n_tiles)
     unsigned long long tile_stride;          // gridDim.x / split, set by the launcher
     unsigned long long ket_xor;
+    unsigned long long* prof;  // development: per-warp phase cycle counters (QFE_PROF=1), else null
+    int stagger;               // cycles CTA b waits before its first tile, times b: spreads the staging bursts of the CTAs over a tile period
     uint8_t run_pos[PLAN_MAX_RUNS];
     uint8_t run_len[PLAN_MAX_RUNS];
     TermConst tc[SWEEP_CONST_TERMS];  // real-coefficient sweeps only
 };
+
+static_assert(sizeof(SweepArgs) <= 32764, "kernel parameter space");
 
 // Fixed shared-memory map (bytes), sized for the largest sweep (2^13 complex128 amplitudes, 2048 complex-coefficient terms):
 // constant offsets let every access be [register + immediate] with nothing to recompute inside the group loop.
@@ -109,7 +115,9 @@ template <int NTH> struct Geo {
     static constexpr uint32_t SM_NATLOC = SM_LOCOFF + PLAN_TABLE * 8;
     static constexpr uint32_t SM_ZOC = SM_NATLOC + PLAN_TABLE * 4;  // z bits of the staged terms outside the tile, packed against the tile number
     static constexpr uint32_t SM_RED = SM_ZOC + CPLX_TERMS * 4;     // block reduction scratch
-    static constexpr uint32_t SM_TOTAL = SM_RED + NW * 16;
+    static constexpr uint32_t SM_PROF = SM_RED + NW * 16;           // development counters (QFE_PROF=1)
+    static constexpr uint32_t SM_TEND = SM_PROF + NW * PROF_PHASES * 8;  // development: when each warp finished the tile's groups
+    static constexpr uint32_t SM_TOTAL = SM_TEND + NW * 8;
 };
 constexpr int SWEEP_MAX_GROUPS = 512;  // ranges per sweep <= 5 skip levels x 2 polarities x 3 kinds
 constexpr int BATCH_MAX_GROUPS = 128;
@@ -588,7 +596,18 @@ __device__ __forceinline__ Terms<real_t, CPLX> make_terms(const SweepArgs& a, co
         return Terms<real_t, false>{a, tile};
 }
 
-template <typename real_t, bool CPLX, int MODE, int NTH>
+// development counters (QFE_PROF=1): lane 0 of every warp adds the cycles since its previous stamp to phase `ph`
+template <bool PROF>
+__device__ __forceinline__ void prof_stamp(unsigned long long* s_prof, long long& t_prev, const int ph) {
+    if (PROF) {
+        const long long now = clock64();
+        if ((threadIdx.x & 31) == 0) s_prof[(threadIdx.x >> 5) * PROF_PHASES + ph] += (unsigned long long)(now - t_prev);
+        t_prev = now;
+    }
+}
+enum { PH_WAIT = 0, PH_ISSUE = 1, PH_GROUPS = 2, PH_SKEW = 3, PH_LOAD = 4, PH_STAGE = 5, PH_ASYNC_TILES = 7 };
+
+template <typename real_t, bool CPLX, int MODE, int NTH, bool PROF = false>
 __global__ void __launch_bounds__(NTH, NT_MAX / NTH) tile_sweep_kernel(const __grid_constant__ SweepArgs a) {
     using G = Geo<NTH>;
     constexpr int NT = NTH, NW = G::NW;
@@ -609,8 +628,22 @@ __global__ void __launch_bounds__(NTH, NT_MAX / NTH) tile_sweep_kernel(const __g
     uint32_t* s_zoc = reinterpret_cast<uint32_t*>(smem + G::SM_ZOC);
     double2* s_acc = reinterpret_cast<double2*>(smem + G::SM_ACC);
     double2* s_red = reinterpret_cast<double2*>(smem + G::SM_RED);
+    unsigned long long* s_prof = reinterpret_cast<unsigned long long*>(smem + G::SM_PROF);
 
     const int tid = threadIdx.x, warp = tid >> 5;
+    if (PROF && tid < NW * PROF_PHASES) s_prof[tid] = 0ull;
+    // development counters: every warp notes when it finished the groups of a tile; after the barrier the latest of these times splits
+    // the tile period into groups (own), skew (waiting for the slowest warp) and staging (from the slowest warp's end to the next groups)
+    long long* s_tend = reinterpret_cast<long long*>(smem + G::SM_TEND);
+    long long t_gs = 0ll, t_end = 0ll, t_last = 0ll;
+    bool have_prev = false;
+    if (a.stagger > 0) {
+        if (tid == 0) {
+            const long long t0 = clock64(), wait = (long long)blockIdx.x * a.stagger;
+            while (clock64() - t0 < wait) __nanosleep(400);
+        }
+        __syncthreads();
+    }
     const cplx_t* __restrict__ ket = reinterpret_cast<const cplx_t*>(a.ket);
     const cplx_t* __restrict__ bra = reinterpret_cast<const cplx_t*>(a.bra);
     cplx_t* __restrict__ yout = reinterpret_cast<cplx_t*>(a.out_vec);
@@ -672,6 +705,11 @@ __global__ void __launch_bounds__(NTH, NT_MAX / NTH) tile_sweep_kernel(const __g
             }
         }
         __syncthreads();  // previous tile fully consumed (also orders the one-time tables)
+        if (PROF && have_prev && (tid & 31) == 0) {
+            t_last = s_tend[0];
+            for (int w = 1; w < NW; ++w) t_last = max(t_last, s_tend[w]);
+            s_prof[warp * PROF_PHASES + PH_SKEW] += (unsigned long long)(t_last - t_end);
+        }
         {
             const uint64_t kbase = base ^ a.ket_xor;
             // the tile is enumerated in natural order (consecutive threads = consecutive amplitudes of a 128 B segment) and
@@ -728,6 +766,10 @@ __global__ void __launch_bounds__(NTH, NT_MAX / NTH) tile_sweep_kernel(const __g
                     }
                 }
             }
+            if (PROF && (tid & 31) == 0) {
+                t_gs = clock64();
+                if (have_prev) s_prof[warp * PROF_PHASES + PH_STAGE] += (unsigned long long)(t_gs - t_last);
+            }
             double2* s_acc_warp = s_acc + (size_t)warp * nG;
             const Terms<real_t, CPLX> terms = make_terms<real_t, CPLX>(a, s_rec, (uint32_t)tile_id);
 #pragma unroll 1
@@ -749,6 +791,13 @@ __global__ void __launch_bounds__(NTH, NT_MAX / NTH) tile_sweep_kernel(const __g
                 else
                     process_range<real_t, CPLX, MODE, KIND_RUNS | KIND_XROW, PLANE>(tile, terms, s_hdr, s_acc_warp, g0, g1, t0, w0, jhi, half, own, acc_re, acc_im, e_re, e_im);
             }
+        }
+        if (PROF && (tid & 31) == 0) {
+            t_end = clock64();
+            s_prof[warp * PROF_PHASES + PH_GROUPS] += (unsigned long long)(t_end - t_gs);
+            s_prof[warp * PROF_PHASES + PH_ASYNC_TILES - 1] += 1ull;  // slot 6: tiles
+            s_tend[warp] = t_end;
+            have_prev = true;
         }
         if (MODE == MODE_APPLY) {
             // the result leaves through the tile, in the natural order it was staged in: 128 B contiguous per 8 threads, and the 16
@@ -797,6 +846,10 @@ __global__ void __launch_bounds__(NTH, NT_MAX / NTH) tile_sweep_kernel(const __g
         }
     }
 
+    if (PROF && a.prof) {
+        __syncthreads();
+        if (tid < NW * PROF_PHASES) atomicAdd(a.prof + tid, s_prof[tid]);
+    }
     if (MODE == MODE_EXPECT) {
         double2 tot = block_reduce_sum(make_double2(e_re, e_im), s_red);
         if (tid == 0) a.partials[blockIdx.x] = tot;
@@ -810,6 +863,181 @@ __global__ void __launch_bounds__(NTH, NT_MAX / NTH) tile_sweep_kernel(const __g
             }
             a.partials[(size_t)g * a.pstride + blockIdx.x] = s;
         }
+    }
+}
+
+// ---- pipelined EXPECT kernel -----------------------------------------------------------------------------------------------------
+// Real-coefficient EXPECT sweeps over full tiles (2^13 amplitudes, 512 threads): the dominant launches of <psi|H|psi>.  Same tile
+// layout and group loops as tile_sweep_kernel, with the serial chain between two tiles shortened (ncu source view of the generic
+// kernel: the warps of a CTA spend 19 % of a 32-qubit step between the last group of one tile and the first group of the next, on a
+// chain of dependent latencies rather than on bandwidth):
+//   * a warp that is done with its groups requests its 16 amplitudes of the CTA's NEXT tile at once (the registers of its own rows
+//     are free then; the lines were sent to L2 a tile earlier), so the load latency passes while the slower warps finish and before
+//     the barrier, not after it;
+//   * tile number -> shard offset is four independent table lookups (the generic kernel walks the runs of the outer mask, a dependent
+//     chain of ~10 steps, twice per tile);
+//   * the own rows are requested first after the barrier, the L2 prefetch of the tile after the next one is issued behind them.
+// Tried and measured slower on this kernel (profiles/r02_phase_async_v1.jsonl, r02_phase3.jsonl): staging half of the next tile with
+// cp.async into a third half-tile region while the groups run -- 16-byte LDGSTS scatter costs more than LDG + STS, and the latency it
+// would hide is not what the tile switch waits for.
+template <typename real_t> struct GeoExpect {
+    using cplx_t = typename CplxOf<real_t>::type;
+    static constexpr int NTH = NT_MAX, NW = NTH / 32;
+    static constexpr uint32_t PLANE = NTH + 1;
+    static constexpr uint32_t SM_TILE = 0;
+    static constexpr uint32_t SM_HDR = ((R * PLANE * (uint32_t)sizeof(cplx_t)) + 15u) & ~15u;
+    static constexpr uint32_t SM_RNG = SM_HDR + 4096;
+    static constexpr uint32_t SM_NATOFF = SM_RNG + 2048;
+    static constexpr uint32_t SM_LOCOFF = SM_NATOFF + PLAN_TABLE * 8;
+    static constexpr uint32_t SM_BASE = SM_LOCOFF + PLAN_TABLE * 8;   // 4 x 128 entries: 7 bits of the tile number -> shard offset
+    static constexpr uint32_t SM_NATLOC = SM_BASE + 4 * 128 * 8;
+    static constexpr uint32_t SM_RED = SM_NATLOC + PLAN_TABLE * 4;
+    static constexpr uint32_t SM_PROF = SM_RED + NW * 16;
+    static constexpr uint32_t SM_TEND = SM_PROF + NW * PROF_PHASES * 8;
+    static constexpr uint32_t SM_TOTAL = SM_TEND + NW * 8;
+};
+static_assert(GeoExpect<double>::SM_TOTAL <= 232448 - 1024, "exceeds the 227 KB of shared memory a CTA may use");
+
+template <typename real_t, bool PROF>
+__global__ void __launch_bounds__(NT_MAX, 1) tile_expect_kernel(const __grid_constant__ SweepArgs a) {
+    using G = GeoExpect<real_t>;
+    constexpr int NT = NT_MAX, NW = G::NW;
+    constexpr uint32_t PLANE = G::PLANE;
+    using cplx_t = typename CplxOf<real_t>::type;
+    extern __shared__ __align__(16) unsigned char smem[];
+    cplx_t* const tile = reinterpret_cast<cplx_t*>(smem + G::SM_TILE);
+    uint2* s_hdr = reinterpret_cast<uint2*>(smem + G::SM_HDR);
+    uint2* s_rng = reinterpret_cast<uint2*>(smem + G::SM_RNG);
+    uint64_t* s_nat_off = reinterpret_cast<uint64_t*>(smem + G::SM_NATOFF);
+    uint64_t* s_loc_off = reinterpret_cast<uint64_t*>(smem + G::SM_LOCOFF);
+    uint64_t* s_base = reinterpret_cast<uint64_t*>(smem + G::SM_BASE);
+    uint32_t* s_nat_loc = reinterpret_cast<uint32_t*>(smem + G::SM_NATLOC);
+    double2* s_red = reinterpret_cast<double2*>(smem + G::SM_RED);
+    unsigned long long* s_prof = reinterpret_cast<unsigned long long*>(smem + G::SM_PROF);
+    long long* s_tend = reinterpret_cast<long long*>(smem + G::SM_TEND);  // development counters, as in tile_sweep_kernel
+    long long t_gs = 0ll, t_end = 0ll, t_last = 0ll;
+    bool have_prev = false;
+
+    const int nG = a.n_groups, nR = a.n_ranges;
+    const int tid = threadIdx.x;
+    const cplx_t* __restrict__ ket = reinterpret_cast<const cplx_t*>(a.ket);
+    const cplx_t* __restrict__ bra = reinterpret_cast<const cplx_t*>(a.bra);
+
+    for (int g = tid; g < nG; g += NT) s_hdr[g] = make_uint2(a.g_hdr[2 * g], a.g_hdr[2 * g + 1]);
+    for (int g = tid; g < nR; g += NT) s_rng[g] = make_uint2(a.r_desc[2 * g], a.r_desc[2 * g + 1]);
+    for (int i = tid; i < PLAN_TABLE; i += NT) {
+        s_nat_off[i] = a.nat_off[i];
+        s_loc_off[i] = a.loc_off[i];
+        s_nat_loc[i] = a.nat_loc[i];
+    }
+    {
+        // entry (k, v): the 7 bits v of the tile number at bit 7k, deposited into the runs of the outer mask
+        unsigned long long rest = (unsigned long long)(tid & 127) << (7 * (tid >> 7));
+        uint64_t b = 0;
+        for (int r = 0; r < a.n_runs; ++r) {
+            const int len = a.run_len[r];
+            b |= (rest & ((1ull << len) - 1ull)) << a.run_pos[r];
+            rest >>= len;
+        }
+        s_base[tid] = b;
+    }
+    if (PROF && tid < NW * PROF_PHASES) s_prof[tid] = 0ull;
+    __syncthreads();
+
+    const uint32_t jhi = (uint32_t)tid << RB, w0 = (uint32_t)tid;
+    double e_re = 0.0, e_im = 0.0;
+    auto base_of = [&](const unsigned long long t) {  // tile numbers stay below 2^28 (shards of at most 2^40 amplitudes, plan_create)
+        return s_base[t & 127] | s_base[128 + ((t >> 7) & 127)] | s_base[256 + ((t >> 14) & 127)] | s_base[384 + ((t >> 21) & 127)];
+    };
+    // the thread's 16 amplitudes of a tile in natural order (idx = tid + u * NT: consecutive threads = consecutive amplitudes of a
+    // 128 B segment); the low 7 index bits are the thread's own
+    const uint64_t off_lo = s_nat_off[tid & 127];
+    const uint32_t loc_lo = s_nat_loc[tid & 127];
+    cplx_t v[R];
+    uint32_t vw[R];  // their words in the tile (the same for every tile; looked up again per tile rather than held across the group loops)
+    auto request = [&](const unsigned long long t) {
+        const uint64_t kb = (base_of(t) ^ a.ket_xor) | off_lo;
+#pragma unroll
+        for (int u = 0; u < R; ++u) v[u] = ld_stream(ket + (kb | s_nat_off[128 + ((tid + u * NT) >> 7)]));
+#pragma unroll
+        for (int u = 0; u < R; ++u) vw[u] = tile_word<PLANE>(loc_lo | s_nat_loc[128 + ((tid + u * NT) >> 7)]);
+    };
+
+    unsigned long long tile_id = a.tile_begin + blockIdx.x;
+    if (tile_id < a.n_tiles) request(tile_id);
+    for (; tile_id < a.n_tiles; tile_id += a.tile_stride) {
+        const unsigned long long next_id = tile_id + a.tile_stride;
+        __syncthreads();  // every partner row of the previous tile has been read
+        if (PROF && have_prev && (tid & 31) == 0) {
+            t_last = s_tend[0];
+            for (int w = 1; w < NW; ++w) t_last = max(t_last, s_tend[w]);
+            s_prof[(tid >> 5) * PROF_PHASES + PH_SKEW] += (unsigned long long)(t_last - t_end);
+        }
+#pragma unroll
+        for (int u = 0; u < R; ++u) tile[vw[u]] = v[u];
+        __syncthreads();
+        {
+            cplx_t own[R];
+            const uint64_t base = a.same_tile ? 0ull : base_of(tile_id);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if (a.same_tile) {
+                    own[r] = tile[(uint32_t)r * PLANE + w0];
+                } else {
+                    const uint32_t j = jhi | (uint32_t)r;
+                    own[r] = bra[base | s_loc_off[j & 127] | s_loc_off[128 + (j >> 7)]];
+                }
+            }
+            // optional (QFE_PREFETCH_DIST=1; off by default: with the request issued ahead of the barrier the L2 prefetch costs more issue
+            // slots than it saves latency, 1.104 s against 1.117 s at 28 qubits): the lines of the next tile -> L2 behind the own rows
+            {
+                if (a.prefetch_dist > 1 && next_id < a.n_tiles) {
+                    const uint64_t nb = base_of(next_id) ^ a.ket_xor;
+#pragma unroll
+                    for (uint32_t idx = 8u * tid; idx < (uint32_t)(R * NT); idx += 8u * NT)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(ket + (nb | s_nat_off[idx & 127] | s_nat_off[128 + (idx >> 7)])));
+                }
+            }
+            if (PROF && (tid & 31) == 0) {
+                t_gs = clock64();
+                if (have_prev) s_prof[(tid >> 5) * PROF_PHASES + PH_STAGE] += (unsigned long long)(t_gs - t_last);
+            }
+            real_t acc_re[R], acc_im[R];  // APPLY only: unused here
+            const Terms<real_t, false> terms{a, (uint32_t)tile_id};
+#pragma unroll 1
+            for (int ri = 0; ri < nR; ++ri) {
+                const uint2 d = s_rng[ri];
+                const uint32_t skipbit = d.y >> RNG_SKIP_SHIFT;
+                const bool half = a.same_tile && skipbit != 0;
+                // the row blocks (warps) of the other polarity hold the partners of these pairs
+                if (half && (((jhi >> skipbit) ^ (d.y >> RNG_POL_SHIFT)) & 1u)) continue;
+                const int g0 = (int)(d.x & 0xffffu), g1 = (int)(d.x >> 16), t0 = (int)(d.y & 0xffffu);
+                const uint32_t kind = (d.y >> RNG_KIND_SHIFT) & 3u;
+                if (kind == KIND_FAST)
+                    process_range<real_t, false, MODE_EXPECT, KIND_FAST, PLANE>(tile, terms, s_hdr, nullptr, g0, g1, t0, w0, jhi, half, own, acc_re, acc_im, e_re, e_im);
+                else if (kind == KIND_RUNS)
+                    process_range<real_t, false, MODE_EXPECT, KIND_RUNS, PLANE>(tile, terms, s_hdr, nullptr, g0, g1, t0, w0, jhi, half, own, acc_re, acc_im, e_re, e_im);
+                else
+                    process_range<real_t, false, MODE_EXPECT, KIND_RUNS | KIND_XROW, PLANE>(tile, terms, s_hdr, nullptr, g0, g1, t0, w0, jhi, half, own, acc_re, acc_im, e_re, e_im);
+            }
+        }
+        if (PROF && (tid & 31) == 0) {
+            t_end = clock64();
+            s_prof[(tid >> 5) * PROF_PHASES + PH_GROUPS] += (unsigned long long)(t_end - t_gs);
+            s_prof[(tid >> 5) * PROF_PHASES + PH_ASYNC_TILES - 1] += 1ull;
+            s_prof[(tid >> 5) * PROF_PHASES + PH_ASYNC_TILES] += 1ull;  // marks this kernel in the counters
+            s_tend[tid >> 5] = t_end;
+            have_prev = true;
+        }
+        // the next tile's amplitudes (the CTA's last tile asks for its own again: unconditional, so the values stay in registers)
+        request(next_id < a.n_tiles ? next_id : tile_id);
+    }
+
+    double2 tot = block_reduce_sum(make_double2(e_re, e_im), s_red);
+    if (tid == 0) a.partials[blockIdx.x] = tot;
+    if (PROF && a.prof) {
+        __syncthreads();
+        if (tid < NW * PROF_PHASES) atomicAdd(a.prof + tid, s_prof[tid]);
     }
 }
 
@@ -991,8 +1219,73 @@ static int launch_tile_n(qfe_ctx* ctx, SweepArgs& args, int grid) {
     return QFE_OK;
 }
 
+// QFE_PIPELINED=0 keeps real-coefficient EXPECT sweeps on the generic kernel; QFE_PROF=1 runs the instrumented instances
+static bool env_flag(const char* name, bool dflt) {
+    const char* e = getenv(name);
+    return e ? (e[0] != '0') : dflt;
+}
+static bool prof_enabled() {
+    static const bool on = env_flag("QFE_PROF", false);
+    return on;
+}
+
+template <typename real_t, bool PROF>
+static int launch_expect_pipelined_p(qfe_ctx* ctx, SweepArgs& args, int grid) {
+    auto kern = tile_expect_kernel<real_t, PROF>;
+    constexpr size_t smem = GeoExpect<real_t>::SM_TOTAL;
+    static int attr_device = -1;
+    if (attr_device != ctx->device) {
+        QFE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_device = ctx->device;
+    }
+    args.tile_stride = (unsigned long long)grid;
+    kern<<<grid, NT_MAX, smem, ctx->stream>>>(args);
+    ctx->launches++;
+    QFE_CUDA(cudaGetLastError());
+    return QFE_OK;
+}
+
+static int prof_buffer(qfe_ctx* ctx, SweepArgs& args) {
+    if (!ctx->prof.p) {
+        QFE_TRY(ctx->prof.alloc(sizeof(unsigned long long) * (NT_MAX / 32) * PROF_PHASES));
+        QFE_CUDA(cudaMemsetAsync(ctx->prof.p, 0, ctx->prof.bytes, ctx->stream));
+    }
+    args.prof = ctx->prof.as<unsigned long long>();
+    return QFE_OK;
+}
+
+// real-coefficient EXPECT sweep over full tiles, one CTA per tile slot
+static bool pipelined_eligible(const SweepArgs& args, bool cplx) {
+    static const bool on = env_flag("QFE_PIPELINED", true);
+    return on && !cplx && args.k == PLAN_MAX_TILE_BITS && args.split == 1;
+}
+static int launch_expect_pipelined(qfe_ctx* ctx, SweepArgs& args, int grid, int dtype) {
+    if (prof_enabled()) {
+        QFE_TRY(prof_buffer(ctx, args));
+        return dtype == QFE_C128 ? launch_expect_pipelined_p<double, true>(ctx, args, grid) : launch_expect_pipelined_p<float, true>(ctx, args, grid);
+    }
+    return dtype == QFE_C128 ? launch_expect_pipelined_p<double, false>(ctx, args, grid) : launch_expect_pipelined_p<float, false>(ctx, args, grid);
+}
+
 template <typename real_t, bool CPLX, int MODE>
 static int launch_tile(qfe_ctx* ctx, SweepArgs& args, int grid) {
+    if constexpr (MODE == MODE_EXPECT && !CPLX && std::is_same<real_t, double>::value) {
+        if (prof_enabled() && sweep_threads(args.k) == NT_MAX) {  // instrumented instance of the synchronously staged kernel
+            QFE_TRY(prof_buffer(ctx, args));
+            auto kern = tile_sweep_kernel<double, false, MODE_EXPECT, NT_MAX, true>;
+            constexpr size_t smem = Geo<NT_MAX>::SM_TOTAL;
+            static int attr_device = -1;
+            if (attr_device != ctx->device) {
+                QFE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                attr_device = ctx->device;
+            }
+            args.tile_stride = (unsigned long long)(grid / std::max(args.split, 1));
+            kern<<<grid, NT_MAX, smem, ctx->stream>>>(args);
+            ctx->launches++;
+            QFE_CUDA(cudaGetLastError());
+            return QFE_OK;
+        }
+    }
     return sweep_threads(args.k) == NT_MAX ? launch_tile_n<real_t, CPLX, MODE, NT_MAX>(ctx, args, grid) : launch_tile_n<real_t, CPLX, MODE, NT_MAX / 2>(ctx, args, grid);
 }
 
@@ -1029,10 +1322,15 @@ static void fill_sweep_args(const qfe_plan* p, const SweepHost& s, int dtype, Sw
     a.n_terms = (int)(s.term_end - s.term_begin);
     a.k = s.k;
     static const int prefetch_dist = [] {
-        const char* pd = getenv("QFE_PREFETCH_DIST");  // development knob
+        const char* pd = getenv("QFE_PREFETCH_DIST");  // development knob (2: also in the pipelined EXPECT kernel)
         return pd ? atoi(pd) : 1;
     }();
     a.prefetch_dist = prefetch_dist;
+    static const int stagger_span = [] {
+        const char* e = getenv("QFE_STAGGER");  // development knob: cycles over which the first tiles of the CTAs are spread
+        return e ? atoi(e) : 0;
+    }();
+    a.stagger = (stagger_span > 0 && s.n_tiles >= 148 * 16) ? stagger_span / 148 : 0;
     a.split = 1;
     a.n_runs = s.n_runs;
     a.tile_begin = 0;
@@ -1141,6 +1439,8 @@ static int run_class_reduce(qfe_ctx* ctx, const qfe_plan* p, int ci, const void*
             a.partials = ctx->partials.as<double2>() + (size_t)vpos * row;
             if (batch)
                 QFE_TRY(launch_tile_d<MODE_BATCH>(ctx, a, grid, sw.complex_w, dtype));
+            else if (pipelined_eligible(a, sw.complex_w))
+                QFE_TRY(launch_expect_pipelined(ctx, a, grid, dtype));
             else
                 QFE_TRY(launch_tile_d<MODE_EXPECT>(ctx, a, grid, sw.complex_w, dtype));
             for (int g = 0; g < n_ranges; ++g) val_slot.push_back(batch ? p->h.g_slot[sw.group_begin + g] : 0);
@@ -1307,6 +1607,18 @@ int qfe_plan_classes(const qfe_plan* p, int32_t* x_hi, int32_t capacity) {
     QFE_REQUIRE(p && x_hi, QFE_ERR_ARG, "null argument");
     QFE_REQUIRE(capacity >= (int32_t)p->h.classes.size(), QFE_ERR_ARG, "qfe_plan_classes: capacity %d < %zu classes", capacity, p->h.classes.size());
     for (size_t i = 0; i < p->h.classes.size(); ++i) x_hi[i] = p->h.classes[i].x_hi;
+    return QFE_OK;
+}
+
+int qfe_dev_phase_cycles(qfe_ctx* ctx, uint64_t* cycles, int reset) {
+    QFE_REQUIRE(ctx && cycles, QFE_ERR_ARG, "qfe_dev_phase_cycles: null argument");
+    QFE_CUDA(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)(NT_MAX / 32) * PROF_PHASES;
+    for (size_t i = 0; i < n; ++i) cycles[i] = 0;
+    if (!ctx->prof.p) return QFE_OK;
+    QFE_CUDA(cudaStreamSynchronize(ctx->stream));
+    QFE_CUDA(cudaMemcpy(cycles, ctx->prof.p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (reset) QFE_CUDA(cudaMemset(ctx->prof.p, 0, n * sizeof(uint64_t)));
     return QFE_OK;
 }
 

@@ -10,6 +10,7 @@ State vectors are torch CUDA tensors (complex128 / complex64); torch is buffer p
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import Sequence
 
 import numpy as np
@@ -39,9 +40,12 @@ def _dtype_code(t) -> int:
 class Plan:
     """Owner of a ``qfe_plan`` handle (sweep schedule of a term set for one shard geometry)."""
 
-    def __init__(self, engine: "Engine", terms: PackedTerms, n_local: int | None = None, shard: int = 0, tile_bits: int = 0):
+    def __init__(self, engine: "Engine", terms: PackedTerms, n_local: int | None = None, shard: int = 0, tile_bits: int = 0, _owned_by_terms: bool = False):
         self.engine = engine
-        self.terms = terms
+        # a plan cached on its term set must not keep that set alive (the set owns the plan); a free-standing plan does
+        self._terms_ref = weakref.ref(terms) if _owned_by_terms else None
+        self._terms_strong = None if _owned_by_terms else terms
+        self.n_slots = terms.n_slots
         self.nqbits = terms.nqbits
         self.n_local = terms.nqbits if n_local is None else n_local
         self.shard = shard
@@ -75,6 +79,13 @@ class Plan:
     def handle(self):
         return self._h
 
+    @property
+    def terms(self) -> PackedTerms:
+        t = self._terms_strong if self._terms_ref is None else self._terms_ref()
+        if t is None:
+            raise RuntimeError("the term set of this plan has been garbage-collected")
+        return t
+
 
 class Engine:
     """One per (process, device).  Owns the ``qfe_ctx``."""
@@ -89,7 +100,6 @@ class Engine:
         h = C.c_void_p()
         check(self.lib.qfe_ctx_create(C.byref(h), device))
         self.ctx = h
-        self._plan_cache: dict = {}
 
     def __del__(self):
         h, self.ctx = getattr(self, "ctx", None), None
@@ -203,11 +213,15 @@ class Engine:
 
     # ---- kernel 2 ----------------------------------------------------------------------------
     def plan(self, terms: PackedTerms, n_local: int | None = None, shard: int = 0, tile_bits: int = 0) -> Plan:
-        key = (id(terms), n_local, shard, tile_bits)
-        p = self._plan_cache.get(key)
-        if p is None or p.terms is not terms:
-            p = Plan(self, terms, n_local, shard, tile_bits)
-            self._plan_cache[key] = p
+        """Sweep schedule of ``terms`` for a shard geometry.  Plans are cached ON the term set (one per engine and geometry), so a plan
+        and its device tables die with the PackedTerms they were built for: callers that make a fresh term set per call (commutator
+        batches, get_matrix, QSE) do not accumulate plans."""
+        cache = terms.__dict__.setdefault("_plans", {})
+        key = (id(self), n_local, shard, tile_bits)
+        p = cache.get(key)
+        if p is None:
+            p = Plan(self, terms, n_local, shard, tile_bits, _owned_by_terms=True)
+            cache[key] = p
         return p
 
     def _check_state(self, psi, n_amps: int):
@@ -227,11 +241,11 @@ class Engine:
         if bra is not None and self._check_state(bra, 1 << plan.nqbits) != dt:
             raise TypeError("bra and ket dtypes differ")
         self._sync_torch()
-        out = np.zeros(2 * plan.terms.n_slots, dtype=np.float64)
+        out = np.zeros(2 * plan.n_slots, dtype=np.float64)
         b = psi if bra is None else bra
         check(self.lib.qfe_expectation_class(self.ctx, plan.handle, 0, C.c_void_p(b.data_ptr()), C.c_void_p(psi.data_ptr()), dt, as_ptr(out, C.c_double)))
         vals = out.view(np.complex128)
-        return complex(vals[0]) if plan.terms.n_slots == 1 else vals.copy()
+        return complex(vals[0]) if plan.n_slots == 1 else vals.copy()
 
     def energy(self, terms_or_plan, psi) -> float:
         return float(np.real(self.expectation(terms_or_plan, psi)))
@@ -286,14 +300,14 @@ class Engine:
         if self._check_state(bra_shard, n_amps) != dt:
             raise TypeError("bra and ket dtypes differ")
         self._sync_torch()
-        out = np.zeros(2 * plan.terms.n_slots, dtype=np.float64)
+        out = np.zeros(2 * plan.n_slots, dtype=np.float64)
         check(
             self.lib.qfe_expectation_class_part(
                 self.ctx, plan.handle, x_hi, C.c_void_p(bra_shard.data_ptr()), C.c_void_p(ket_shard.data_ptr()), dt, part, n_parts, as_ptr(out, C.c_double)
             )
         )
         vals = out.view(np.complex128)
-        return complex(vals[0]) if plan.terms.n_slots == 1 else vals.copy()
+        return complex(vals[0]) if plan.n_slots == 1 else vals.copy()
 
     def apply_class(self, plan: Plan, x_hi: int, ket_shard, y_shard, accumulate: bool, sync: bool = True) -> None:
         """y_shard (+)= H_class(x_hi) ket_shard, where ket_shard is the shard (shard ^ x_hi) of the ket."""
@@ -319,7 +333,7 @@ class Engine:
         if scratch is None:
             scratch = torch.empty_like(psi)
         self._sync_torch()
-        g = np.zeros(pool_plan.terms.n_slots, dtype=np.float64)
+        g = np.zeros(pool_plan.n_slots, dtype=np.float64)
         check(
             self.lib.qfe_commutator_gradients(
                 self.ctx, h_plan.handle, pool_plan.handle, C.c_void_p(psi.data_ptr()), C.c_void_p(scratch.data_ptr()), dt, as_ptr(g, C.c_double)
@@ -373,6 +387,7 @@ class Engine:
         psi = torch.empty(1 << n_local, dtype=dtype, device=f"cuda:{self.device}")
         self._sync_torch()
         check(self.lib.qfe_vec_product_state(self.ctx, C.c_void_p(psi.data_ptr()), n_local, shard, nqbits, as_ptr(ab.view(np.float64), C.c_double), _dtype_code(psi)))
+        self.sync()
         return psi
 
     def basis_state(self, nqbits: int, index: int, dtype=None, n_local: int | None = None, shard: int = 0):
@@ -385,6 +400,7 @@ class Engine:
         psi = torch.empty(N, dtype=dtype, device=f"cuda:{self.device}")
         self._sync_torch()
         check(self.lib.qfe_vec_basis_state(self.ctx, C.c_void_p(psi.data_ptr()), N, _dtype_code(psi), local if 0 <= local < N else -1))
+        self.sync()  # like random_state / product_state: the vector is complete when the call returns, whatever stream reads it next
         return psi
 
     # ---- state evolution ----------------------------------------------------

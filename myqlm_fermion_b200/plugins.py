@@ -80,8 +80,7 @@ class AdaptVQEGradients:
         self.commutators = commutators
         self.mode = mode
         self._pool_terms = None
-        self._h_key = None
-        self._h_terms = None
+        self._commutator_batch = None  # (observable the commutators were expanded for, concatenated term set)
 
     @staticmethod
     def _compute_commutators(observable: SpinHamiltonian, pool: Sequence[SpinHamiltonian]):
@@ -90,16 +89,19 @@ class AdaptVQEGradients:
     def gradients(self, observable: SpinHamiltonian, psi) -> np.ndarray:
         eng = self.engine
         if self.mode == "commutators":
-            if self.commutators is None:
+            # commutators handed in by the caller are used as they are (adapt_vqe.py:40,169-170); the ones expanded here belong to one
+            # observable (held by reference, so its identity cannot be recycled) and are expanded again for another
+            if self.commutators is None or (self._commutator_batch is not None and self._commutator_batch[0] is not observable):
                 self.commutators = self._compute_commutators(observable, self.pool)
-            batch = eng.concat([c.packed(eng) for c in self.commutators])
-            vals = np.atleast_1d(eng.expectation(batch, psi))
+                self._commutator_batch = None
+            if self._commutator_batch is None:
+                self._commutator_batch = (observable, eng.concat([c.packed(eng) for c in self.commutators]))
+            vals = np.atleast_1d(eng.expectation(self._commutator_batch[1], psi))
             return np.real(-1j * vals)
         if self._pool_terms is None:
             self._pool_terms = eng.concat([op.packed(eng) for op in self.pool])
-        if self._h_key != id(observable):
-            self._h_terms, self._h_key = observable.packed(eng), id(observable)
-        return eng.commutator_gradients(self._h_terms, self._pool_terms, psi)
+        # observable.packed() is cached on the object and rebuilt when its constant changed: ask every time
+        return eng.commutator_gradients(observable.packed(eng), self._pool_terms, psi)
 
     def select(self, energy_gradients: np.ndarray):
         """(operator index or None, gradient norm) as adapt_vqe.py:186-195."""
@@ -127,38 +129,39 @@ class SeqOptim:
         self.n_evaluations = 0
 
     def optimize(self, var_names: Sequence[str], evaluate: Callable[[dict], float]):
-        """``evaluate(params: dict) -> energy`` plays the role of ``Optimizer.evaluate``."""
-        n_params = len(var_names)
-        x0 = list(self.x0) if self.x0 is not None else list(np.random.random(n_params))
-        params = {var_names[i]: val for i, val in enumerate(x0)}
+        """``evaluate(params: dict) -> energy`` plays the role of ``Optimizer.evaluate``.
 
-        def ev(p):
+        One coordinate update of rotosolve: E(theta_d) = a sin(theta_d + b) + c along every angle, so the three values
+        E(theta), E(theta + pi/2), E(theta - pi/2) fix the minimiser theta - pi/2 - atan2(2E - E+ - E-, E+ - E-)
+        (sequential_optimization.py:125-135); the energy at the new angle becomes the E of the next coordinate."""
+        names = [str(v) for v in var_names]
+        theta = np.array(self.x0 if self.x0 is not None else np.random.random(len(names)), dtype=object)
+
+        def energy_at(angles) -> float:
             self.n_evaluations += 1
             try:
-                scaled = {k: v * self.coeff for k, v in p.items()}
+                scaled = {name: angle * self.coeff for name, angle in zip(names, angles)}
             except Exception as exc:
                 raise ValueError("Parameters must be real-valued!") from exc
-            return evaluate(scaled)
+            return np.real(evaluate(scaled))
 
-        cf = ev(params)
-        for k in range(self.ncycles_roto):
+        def shifted(d: int, delta: float):
+            out = theta.copy()
+            out[d] = out[d] + delta
+            return out
+
+        energy = evaluate({name: angle * self.coeff for name, angle in zip(names, theta)})
+        self.n_evaluations += 1
+        for cycle in range(self.ncycles_roto):
             if self.verbose:
-                print("-------Optimization cycle #%i-----------" % (k + 1))
-            for d in range(n_params):
-                key = str(var_names[d])
-                plus = dict(params)
-                plus[key] = params[key] + math.pi / 2
-                cf_plus = np.real(ev(plus))
-                minus = dict(params)
-                minus[key] = params[key] - math.pi / 2
-                cf_minus = np.real(ev(minus))
-                new = dict(params)
-                new[key] = params[key] - math.pi / 2 - math.atan2(2 * cf - cf_plus - cf_minus, cf_plus - cf_minus)
-                cf = np.real(ev(new))
-                params = new
+                print("-------Optimization cycle #%i-----------" % (cycle + 1))
+            for d in range(len(names)):
+                e_plus, e_minus = energy_at(shifted(d, math.pi / 2)), energy_at(shifted(d, -math.pi / 2))
+                theta = shifted(d, -math.pi / 2 - math.atan2(2 * energy - e_plus - e_minus, e_plus - e_minus))
+                energy = energy_at(theta)
             if self.verbose:
-                print("current cost:", cf)
-        result = SeqOptimResult(params.values(), cf)
+                print("current cost:", energy)
+        result = SeqOptimResult(list(theta), energy)
         return result.fun, list(result.x), result
 
 

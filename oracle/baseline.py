@@ -37,20 +37,24 @@ def sample_terms(n: int, seed: int = 1234, encoding: str = "jordan-wigner"):
     return triples, k
 
 
+def reference_matrix(n: int, triples, constant, workers: int = 1, pool: ProcessPoolExecutor | None = None):
+    """get_matrix(sparse=True) of the term list; with a pool the term list is split across processes and the partial matrices added."""
+    if workers <= 1 or pool is None:
+        return spin.spin_get_matrix(n, triples, constant, sparse=True)
+    chunks = [triples[i::workers] for i in range(workers)]
+    parts = list(pool.map(_partial_matrix, [(n, ch) for ch in chunks if ch]))
+    mat = parts[0]
+    for p in parts[1:]:
+        mat = mat + p
+    import scipy.sparse as sp
+
+    return (mat + constant * sp.identity(2**n, dtype=complex, format="csr")).tocsr()
+
+
 def reference_energy(n: int, triples, constant, psi: np.ndarray, workers: int = 1, pool: ProcessPoolExecutor | None = None):
     """(energy, t_build, t_eval): get_matrix(sparse=True) then vdot(psi, H psi)."""
     t0 = time.perf_counter()
-    if workers <= 1 or pool is None:
-        mat = spin.spin_get_matrix(n, triples, constant, sparse=True)
-    else:
-        chunks = [triples[i::workers] for i in range(workers)]
-        parts = list(pool.map(_partial_matrix, [(n, ch) for ch in chunks if ch]))
-        mat = parts[0]
-        for p in parts[1:]:
-            mat = mat + p
-        import scipy.sparse as sp
-
-        mat = mat + constant * sp.identity(2**n, dtype=complex, format="csr")
+    mat = reference_matrix(n, triples, constant, workers, pool)
     t1 = time.perf_counter()
     e = np.vdot(psi, mat.dot(psi))
     t2 = time.perf_counter()
