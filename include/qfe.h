@@ -42,7 +42,8 @@ typedef enum {
     QFE_ERR_CUDA = -2,        /* CUDA runtime error                                            */
     QFE_ERR_OOM = -3,         /* host or device allocation failed                              */
     QFE_ERR_UNSUPPORTED = -4, /* e.g. more than 64 qubits, unknown encoding (KeyError)         */
-    QFE_ERR_STATE = -5        /* handle used in the wrong state                                */
+    QFE_ERR_STATE = -5,       /* handle used in the wrong state                                */
+    QFE_ERR_COMM = -6         /* NCCL error / NCCL not available                               */
 } qfe_status;
 
 enum { QFE_ENC_JW = 0, QFE_ENC_BK = 1, QFE_ENC_PARITY = 2 };
@@ -112,6 +113,8 @@ int qfe_plan_geometry(const qfe_plan* p, int* nqbits, int* n_local);
  * then needs each pair of shards (r, r^x_hi) on one of the two ranks only                                                    */
 int qfe_plan_hermitian(const qfe_plan* p, int* hermitian);
 int qfe_plan_work(const qfe_plan* p, int64_t* half_groups, int64_t* full_groups, int64_t* half_terms, int64_t* full_terms);
+/* operators (output slots) of the planned term set: 1, or K for a qfe_terms_concat batch        */
+int qfe_plan_slots(const qfe_plan* p, int64_t* n_slots);
 /* the distinct x_hi classes, ascending (class 0 first when present)                            */
 int qfe_plan_classes(const qfe_plan* p, int32_t* x_hi, int32_t capacity);
 int qfe_plan_destroy(qfe_plan* p);
@@ -167,6 +170,41 @@ int qfe_vec_product_state(qfe_ctx* ctx, void* x, int n_local, int shard, int nqb
  * not hold the occupied amplitude).  Replaces the X-gate layer the reference prepends to its ansatz circuits
  * (Hartree-Fock state, qat/fermion/chemistry/ucc.py:291-343)                                                                    */
 int qfe_vec_basis_state(qfe_ctx* ctx, void* x, int64_t n_amps, int dtype, int64_t index);
+
+/* ---- multi-GPU: one process per GPU, the statevector sharded by its high qubits -----------------------------------
+ * The context owns an NCCL communicator.  Rank 0 makes a unique id, the host hands it to every rank by any channel (the Python host:
+ * torch.distributed broadcast; an MPI or file rendezvous works as well), then every rank calls qfe_comm_init -- collectively.  Plans
+ * are created with n_local = nqbits - log2(nranks) and shard = rank.  `partner` is device scratch owned by the caller for the shard of
+ * the rank ^ x_hi partner: one shard (exchange, then sweeps) or two (partner_bytes >= 2 shards: the exchange of the next class runs
+ * on a second stream while the sweeps of the current class run).  Every call below is collective over the communicator, and results
+ * are identical on every rank.  NCCL is bound at run time (dlopen of libnccl.so.2; QFE_NCCL_LIB overrides): QFE_ERR_COMM if missing. */
+int qfe_comm_unique_id(uint8_t id[128]);
+int qfe_comm_init(qfe_ctx* ctx, const uint8_t id[128], int rank, int nranks);
+int qfe_comm_info(const qfe_ctx* ctx, int* rank, int* nranks, int* nccl_version, int64_t* exchanges, int64_t* exchanged_bytes);
+int qfe_comm_destroy(qfe_ctx* ctx);
+/* attribution aid: the x_hi classes of the last qfe_expectation_sharded[_host] on this rank and the host milliseconds each took
+ * (wait for the exchange + sweeps); n = number of classes, at most `capacity` are written                                          */
+int qfe_comm_class_times(const qfe_ctx* ctx, int32_t* x_hi, double* ms, int32_t capacity, int32_t* n);
+/* in-place sum of n host doubles over the ranks (one ncclAllReduce); identity without a communicator                               */
+int qfe_allreduce_sum(qfe_ctx* ctx, double* values, int n);
+/* partner <- the shard of rank ^ x_hi of the vector `shard` belongs to (ncclSend + ncclRecv in one group, on the ctx stream)        */
+int qfe_exchange_shard(qfe_ctx* ctx, const void* shard, void* partner, int64_t n_amps, int dtype, int x_hi);
+/* <bra|H|ket> of the whole register (bra_shard NULL: <ket|H|ket>; a Hermitian single-operator plan then splits every non-local class
+ * between the two ranks of a pair); out = 2*n_slots doubles.  Replaces the same call sites as qfe_expectation_class.                */
+int qfe_expectation_sharded(qfe_ctx* ctx, const qfe_plan* p, const void* bra_shard, const void* ket_shard, void* partner, int64_t partner_bytes,
+                            int dtype, double* out);
+/* the same with this rank's shard arriving from HOST memory: uploaded into shard_dev behind the sweeps of the local class             */
+int qfe_expectation_sharded_host(qfe_ctx* ctx, const qfe_plan* p, const void* shard_host, void* shard_dev, void* partner, int64_t partner_bytes,
+                                 int dtype, double out[2]);
+/* y_shard = this rank's shard of H|ket>                                                                                             */
+int qfe_apply_sharded(qfe_ctx* ctx, const qfe_plan* p, const void* ket_shard, void* y_shard, void* partner, int64_t partner_bytes, int dtype);
+/* ADAPT-VQE gradient sweep on a sharded state (qat/plugins/adapt_vqe.py:181-185); scratch = one shard (H psi)                        */
+int qfe_commutator_gradients_sharded(qfe_ctx* ctx, const qfe_plan* h_plan, const qfe_plan* pool_plan, const void* psi_shard, void* scratch,
+                                     void* partner, int64_t partner_bytes, int dtype, double* grads);
+int qfe_vec_dot_sharded(qfe_ctx* ctx, const void* a, const void* b, int64_t n_amps, int dtype, double out[2]); /* <a|b>, all-reduced */
+/* qfe_lanczos on shards (work = 3 shards): the dots and norms of the recurrence are all-reduced                                     */
+int qfe_lanczos_sharded(qfe_ctx* ctx, const qfe_plan* p, void* v, void* work, void* partner, int64_t partner_bytes, int max_iter, double tol,
+                        int dtype, int want_vector, double* eval, int* iters, double* resid);
 
 /* ---- state evolution ----------------------------------------------------------------------------------------------
  * In place psi <- exp(-i theta[K-1] P[K-1]) ... exp(-i theta[0] P[0]) psi on an unsharded state of nqbits qubits, with

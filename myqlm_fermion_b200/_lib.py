@@ -14,7 +14,7 @@ _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "libqfe.so"
 
 QFE_OK = 0
-QFE_ERR_ARG, QFE_ERR_CUDA, QFE_ERR_OOM, QFE_ERR_UNSUPPORTED, QFE_ERR_STATE = -1, -2, -3, -4, -5
+QFE_ERR_ARG, QFE_ERR_CUDA, QFE_ERR_OOM, QFE_ERR_UNSUPPORTED, QFE_ERR_STATE, QFE_ERR_COMM = -1, -2, -3, -4, -5, -6
 ENC = {"jordan-wigner": 0, "bravyi-kitaev": 1, "parity": 2}
 C128, C64 = 0, 1
 
@@ -47,6 +47,7 @@ SIGNATURES = {
     "qfe_plan_hermitian": (C.c_int, [C.c_void_p, c_int_p]),
     "qfe_plan_work": (C.c_int, [C.c_void_p, c_i64_p, c_i64_p, c_i64_p, c_i64_p]),
     "qfe_plan_geometry": (C.c_int, [C.c_void_p, c_int_p, c_int_p]),
+    "qfe_plan_slots": (C.c_int, [C.c_void_p, c_i64_p]),
     "qfe_plan_classes": (C.c_int, [C.c_void_p, c_i32_p, C.c_int32]),
     "qfe_plan_destroy": (C.c_int, [C.c_void_p]),
     "qfe_expectation_class": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, c_double_p]),
@@ -65,6 +66,20 @@ SIGNATURES = {
     "qfe_vec_fill_random": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_uint64, C.c_uint64]),
     "qfe_vec_product_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, c_double_p, C.c_int]),
     "qfe_vec_basis_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int64]),
+    "qfe_comm_unique_id": (C.c_int, [c_u8_p]),
+    "qfe_comm_init": (C.c_int, [C.c_void_p, c_u8_p, C.c_int, C.c_int]),
+    "qfe_comm_info": (C.c_int, [C.c_void_p, c_int_p, c_int_p, c_int_p, c_i64_p, c_i64_p]),
+    "qfe_comm_class_times": (C.c_int, [C.c_void_p, c_i32_p, c_double_p, C.c_int32, c_i32_p]),
+    "qfe_comm_destroy": (C.c_int, [C.c_void_p]),
+    "qfe_allreduce_sum": (C.c_int, [C.c_void_p, c_double_p, C.c_int]),
+    "qfe_exchange_shard": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int]),
+    "qfe_expectation_sharded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, c_double_p]),
+    "qfe_expectation_sharded_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, c_double_p]),
+    "qfe_apply_sharded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]),
+    "qfe_commutator_gradients_sharded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, c_double_p]),
+    "qfe_vec_dot_sharded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, c_double_p]),
+    "qfe_lanczos_sharded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_int, C.c_int, c_double_p,
+                                      c_int_p, c_double_p]),
     "qfe_pauli_rotations": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, c_u64_p, c_u64_p, c_double_p, C.c_void_p, C.c_int]),
 }
 

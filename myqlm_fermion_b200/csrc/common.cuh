@@ -7,8 +7,10 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <new>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/qfe.h"
@@ -87,6 +89,15 @@ struct qfe_ctx {
     qfe::DevBuf slabs;      // per-part partial results of APPLY sweeps whose tiles are shared by several CTAs (small shards)
     void* pinned = nullptr; // small pinned host buffer for scalar read-back
     size_t pinned_bytes = 0;
+    // multi-GPU (sharded.cu): the NCCL communicator of this rank, a stream for the shard exchanges and the events that order them
+    void* comm = nullptr;   // ncclComm_t
+    int comm_rank = 0, comm_nranks = 1;
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t comm_ev[3] = {nullptr, nullptr, nullptr};  // [b]: partner buffer b has arrived; [2]: compute stream position at the start of a walk
+    cudaEvent_t comm_done[2] = {nullptr, nullptr};         // [b]: the sweeps that read partner buffer b are enqueued
+    qfe::DevBuf comm_scratch;                              // scalars on their way through an all-reduce
+    int64_t exchanges = 0, exchanged_bytes = 0;
+    std::vector<std::pair<int, double>> class_ms;          // last qfe_expectation_sharded*: (x_hi, host milliseconds incl. the wait for the exchange)
 };
 
 struct qfe_terms {
@@ -121,5 +132,14 @@ int radix_sort_terms(qfe_ctx* ctx, uint64_t* x, uint64_t* z, uint32_t* owner, ui
 
 // vals[r] = sum over blocks of partials[r * n_blocks + b] in a fixed order (sweep.cu)
 int reduce_to_vals(qfe_ctx* ctx, const double2* partials, int n_ranges, int n_blocks, double2* vals);
+
+// Lanczos recurrence on an abstract operator (lanczos.cu): `apply(cur, w)` enqueues w = H cur on ctx->stream for this rank's part of the
+// vectors (n_amps amplitudes each), `reduce(vals, n)` sums host scalars over the ranks (identity on one GPU).
+struct LanczosOps {
+    std::function<int(const void*, void*)> apply;
+    std::function<int(double*, int)> reduce;
+};
+int lanczos_run(qfe_ctx* ctx, const LanczosOps& ops, int64_t n_amps, void* v, void* work, int max_iter, double tol, int dtype, int want_vector,
+                double* eval, int* iters, double* resid);
 
 }  // namespace qfe

@@ -326,6 +326,85 @@ void lowest_eigenvector(const std::vector<double>& a, const std::vector<double>&
 }
 
 }  // namespace
+
+int lanczos_run(qfe_ctx* ctx, const LanczosOps& ops, int64_t N, void* v, void* work, int max_iter, double tol, int dtype, int want_vector, double* eval,
+                int* iters, double* resid) {
+    QFE_REQUIRE(max_iter >= 1, QFE_ERR_ARG, "qfe_lanczos: max_iter must be >= 1");
+    const size_t bytes = (size_t)N * (dtype == QFE_C128 ? 16 : 8);
+    char* wk = (char*)work;
+    void* buf[3] = {wk, wk + bytes, wk + 2 * bytes};
+
+    std::vector<double> alpha, beta;
+    double theta = 0.0, res = 0.0;
+    int m_done = 0;
+    std::vector<double> y;
+
+    for (int pass = 0; pass < (want_vector ? 2 : 1); ++pass) {
+        // v_cur = start / ||start||
+        double nn[2];
+        QFE_TRY(qfe_vec_dot(ctx, v, v, N, dtype, nn));
+        QFE_TRY(ops.reduce(nn, 2));
+        QFE_REQUIRE(nn[0] > 0.0, QFE_ERR_ARG, "qfe_lanczos: start vector has zero norm");
+        void *cur = buf[0], *prev = buf[1], *w = buf[2];
+        QFE_TRY(DISPATCH(dtype, axpy_impl, ctx, 1.0 / sqrt(nn[0]), 0.0, v, cur, N, 0));
+        if (pass == 1) QFE_TRY(DISPATCH(dtype, axpy_impl, ctx, y[0], 0.0, cur, v, N, 0));
+        const int m_target = pass == 0 ? max_iter : m_done;
+        double beta_prev = 0.0;
+        for (int j = 0; j < m_target; ++j) {
+            QFE_TRY(ops.apply(cur, w));
+            double a_j;
+            if (pass == 0) {
+                double d[2];
+                QFE_TRY(qfe_vec_dot(ctx, cur, w, N, dtype, d));
+                QFE_TRY(ops.reduce(d, 2));
+                a_j = d[0];
+                alpha.push_back(a_j);
+            } else {
+                a_j = alpha[j];
+            }
+            double nrm2 = 0.0;
+            QFE_TRY(DISPATCH(dtype, update_impl, ctx, w, cur, j ? prev : nullptr, a_j, beta_prev, N, &nrm2));
+            QFE_TRY(ops.reduce(&nrm2, 1));
+            double b_j = sqrt(nrm2);
+            if (pass == 0) {
+                beta.push_back(b_j);
+                const int m = j + 1;
+                const bool check = (m % 5 == 0) || m == max_iter || b_j <= 1e-14 * std::max(1.0, fabs(a_j));
+                if (check) {
+                    theta = lowest_eigenvalue(alpha, beta, m);
+                    lowest_eigenvector(alpha, beta, m, theta, y);
+                    res = fabs(b_j * y[m - 1]);
+                    m_done = m;
+                    if (res <= tol * std::max(1.0, fabs(theta)) || b_j <= 1e-14 * std::max(1.0, fabs(a_j))) break;
+                }
+                m_done = m;
+            } else {
+                b_j = beta[j];
+                if (j + 1 >= m_done) break;
+            }
+            if (b_j == 0.0) break;
+            // v_next = w / beta_j ; rotate buffers
+            QFE_TRY(DISPATCH(dtype, scale_impl, ctx, 1.0 / b_j, 0.0, w, N));
+            void* t = prev;
+            prev = cur;
+            cur = w;
+            w = t;
+            beta_prev = b_j;
+            if (pass == 1) QFE_TRY(DISPATCH(dtype, axpy_impl, ctx, y[j + 1], 0.0, cur, v, N, 1));
+        }
+        if (pass == 0) {
+            theta = lowest_eigenvalue(alpha, beta, m_done);
+            lowest_eigenvector(alpha, beta, m_done, theta, y);
+            res = fabs(beta[m_done - 1] * y[m_done - 1]);
+        }
+    }
+    QFE_CUDA(cudaStreamSynchronize(ctx->stream));
+    *eval = theta;
+    if (iters) *iters = m_done;
+    if (resid) *resid = res;
+    return QFE_OK;
+}
+
 }  // namespace qfe
 
 using namespace qfe;
@@ -383,82 +462,14 @@ int qfe_lanczos(qfe_ctx* ctx, const qfe_plan* p, void* v, void* work, int max_it
                 int* iters, double* resid) {
     QFE_REQUIRE(ctx && p && v && work && eval, QFE_ERR_ARG, "qfe_lanczos: null argument");
     QFE_REQUIRE(dtype == QFE_C128 || dtype == QFE_C64, QFE_ERR_ARG, "unknown dtype %d", dtype);
-    QFE_REQUIRE(max_iter >= 1, QFE_ERR_ARG, "qfe_lanczos: max_iter must be >= 1");
     QFE_CUDA(cudaSetDevice(ctx->device));
     int n = 0, n_local = 0;
     QFE_TRY(qfe_plan_geometry(p, &n, &n_local));
-    QFE_REQUIRE(n == n_local, QFE_ERR_STATE, "qfe_lanczos needs an unsharded plan (the sharded driver lives in the Python host)");
-    const int64_t N = int64_t(1) << n;
-    const size_t bytes = (size_t)N * (dtype == QFE_C128 ? 16 : 8);
-    char* wk = (char*)work;
-    void* buf[3] = {wk, wk + bytes, wk + 2 * bytes};
-
-    std::vector<double> alpha, beta;
-    double theta = 0.0, res = 0.0;
-    int m_done = 0;
-    std::vector<double> y;
-
-    for (int pass = 0; pass < (want_vector ? 2 : 1); ++pass) {
-        // v_cur = start / ||start||
-        double nn[2];
-        QFE_TRY(qfe_vec_dot(ctx, v, v, N, dtype, nn));
-        QFE_REQUIRE(nn[0] > 0.0, QFE_ERR_ARG, "qfe_lanczos: start vector has zero norm");
-        void *cur = buf[0], *prev = buf[1], *w = buf[2];
-        QFE_TRY(DISPATCH(dtype, axpy_impl, ctx, 1.0 / sqrt(nn[0]), 0.0, v, cur, N, 0));
-        if (pass == 1) QFE_TRY(DISPATCH(dtype, axpy_impl, ctx, y[0], 0.0, cur, v, N, 0));
-        const int m_target = pass == 0 ? max_iter : m_done;
-        double beta_prev = 0.0;
-        for (int j = 0; j < m_target; ++j) {
-            QFE_TRY(qfe_apply(ctx, p, cur, w, dtype));
-            double a_j;
-            if (pass == 0) {
-                double d[2];
-                QFE_TRY(qfe_vec_dot(ctx, cur, w, N, dtype, d));
-                a_j = d[0];
-                alpha.push_back(a_j);
-            } else {
-                a_j = alpha[j];
-            }
-            double nrm2 = 0.0;
-            QFE_TRY(DISPATCH(dtype, update_impl, ctx, w, cur, j ? prev : nullptr, a_j, beta_prev, N, &nrm2));
-            double b_j = sqrt(nrm2);
-            if (pass == 0) {
-                beta.push_back(b_j);
-                const int m = j + 1;
-                const bool check = (m % 5 == 0) || m == max_iter || b_j <= 1e-14 * std::max(1.0, fabs(a_j));
-                if (check) {
-                    theta = lowest_eigenvalue(alpha, beta, m);
-                    lowest_eigenvector(alpha, beta, m, theta, y);
-                    res = fabs(b_j * y[m - 1]);
-                    m_done = m;
-                    if (res <= tol * std::max(1.0, fabs(theta)) || b_j <= 1e-14 * std::max(1.0, fabs(a_j))) break;
-                }
-                m_done = m;
-            } else {
-                b_j = beta[j];
-                if (j + 1 >= m_done) break;
-            }
-            if (b_j == 0.0) break;
-            // v_next = w / beta_j ; rotate buffers
-            QFE_TRY(DISPATCH(dtype, scale_impl, ctx, 1.0 / b_j, 0.0, w, N));
-            void* t = prev;
-            prev = cur;
-            cur = w;
-            w = t;
-            beta_prev = b_j;
-            if (pass == 1) QFE_TRY(DISPATCH(dtype, axpy_impl, ctx, y[j + 1], 0.0, cur, v, N, 1));
-        }
-        if (pass == 0) {
-            theta = lowest_eigenvalue(alpha, beta, m_done);
-            lowest_eigenvector(alpha, beta, m_done, theta, y);
-            res = fabs(beta[m_done - 1] * y[m_done - 1]);
-        }
-    }
-    QFE_CUDA(cudaStreamSynchronize(ctx->stream));
-    *eval = theta;
-    if (iters) *iters = m_done;
-    if (resid) *resid = res;
-    return QFE_OK;
+    QFE_REQUIRE(n == n_local, QFE_ERR_STATE, "qfe_lanczos needs an unsharded plan; use qfe_lanczos_sharded");
+    LanczosOps ops;
+    ops.apply = [&](const void* cur, void* w) { return qfe_apply(ctx, p, cur, w, dtype); };
+    ops.reduce = [](double*, int) { return (int)QFE_OK; };
+    return lanczos_run(ctx, ops, int64_t(1) << n, v, work, max_iter, tol, dtype, want_vector, eval, iters, resid);
 }
 
 }  // extern "C"

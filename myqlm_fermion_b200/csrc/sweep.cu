@@ -1603,6 +1603,12 @@ int qfe_plan_geometry(const qfe_plan* p, int* nqbits, int* n_local) {
     return QFE_OK;
 }
 
+int qfe_plan_slots(const qfe_plan* p, int64_t* n_slots) {
+    QFE_REQUIRE(p && n_slots, QFE_ERR_ARG, "null argument");
+    *n_slots = p->h.n_slots;
+    return QFE_OK;
+}
+
 int qfe_plan_classes(const qfe_plan* p, int32_t* x_hi, int32_t capacity) {
     QFE_REQUIRE(p && x_hi, QFE_ERR_ARG, "null argument");
     QFE_REQUIRE(capacity >= (int32_t)p->h.classes.size(), QFE_ERR_ARG, "qfe_plan_classes: capacity %d < %zu classes", capacity, p->h.classes.size());

@@ -456,6 +456,7 @@ int qfe_ctx_sync(qfe_ctx* ctx) {
 int qfe_ctx_destroy(qfe_ctx* ctx) {
     if (!ctx) return QFE_OK;
     cudaSetDevice(ctx->device);
+    qfe_comm_destroy(ctx);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);

@@ -1,5 +1,11 @@
-"""Statevector sharded over the ranks of one node: one process per GPU, ``torch.distributed`` for the
-plumbing (NCCL over NVLink/NVSwitch on the GPU box, gloo in the CPU tests).
+"""Statevector sharded over the ranks of one node: one process per GPU.
+
+On the GPU box (``torch.distributed`` backend "nccl") ``ShardedEngine`` is a ctypes shim: the class loop, the pairwise
+``ncclSend``/``ncclRecv`` exchanges, the overlap of the next exchange with the current sweeps, the scalar all-reduce and the
+sharded Lanczos all live behind the C ABI (``qfe_*_sharded`` in include/qfe.h, csrc/sharded.cu), on an NCCL communicator the
+``qfe_ctx`` owns; torch.distributed only carries the 128-byte NCCL id to the ranks.  With any other backend (gloo in the CPU
+tests, where the compute backend is the plan interpreter of tests/cpu_backend.py) the same class loop runs here in Python over
+``torch.distributed`` point-to-point calls: that mirror is what the world-size-2/4 CPU tests cover.
 
 Rank r holds the 2^(n-g) amplitudes whose g most significant index bits (= qubits 0..g-1, because
 qubit 0 is the MSB: /root/reference/qat/fermion/hamiltonians.py:231-235) equal r.  A Pauli term whose
@@ -12,6 +18,8 @@ The reference has no distributed path at all; this module is new structure aroun
 """
 
 from __future__ import annotations
+
+import ctypes as C
 
 import numpy as np
 
@@ -46,8 +54,59 @@ class ShardedEngine:
         self.nqbits = nqbits
         self.n_local = nqbits - g
         self._partner = None
-        self.exchanges = 0
-        self.exchanged_bytes = 0
+        self._work = None
+        self._exchanges = 0
+        self._exchanged_bytes = 0
+        # native path: the backend is the CUDA engine and the ranks talk NCCL -> everything below the call is C (csrc/sharded.cu)
+        self.native = hasattr(backend, "lib") and hasattr(backend, "ctx") and dist.get_backend(group) == "nccl"
+        if self.native:
+            self._init_native_comm()
+
+    def _init_native_comm(self) -> None:
+        """Rank 0 draws an NCCL unique id (qfe_comm_unique_id), torch.distributed hands it to every rank, every rank joins
+        (qfe_comm_init).  A context keeps its communicator: a second ShardedEngine on the same engine reuses it."""
+        import torch
+
+        from ._lib import check
+
+        dist = _dist()
+        be = self.backend
+        if getattr(be, "_comm_world", None) is not None:
+            if be._comm_world != (self.rank, self.world):
+                raise RuntimeError(f"the engine's communicator is rank {be._comm_world[0]} of {be._comm_world[1]}, this group is rank {self.rank} of {self.world}")
+            return
+        uid = np.zeros(128, dtype=np.uint8)
+        if self.rank == 0:
+            check(be.lib.qfe_comm_unique_id(uid.ctypes.data_as(C.POINTER(C.c_uint8))))
+        t = torch.from_numpy(uid).to(f"cuda:{be.device}")
+        src = dist.get_global_rank(self.group, 0) if self.group is not None else 0
+        dist.broadcast(t, src=src, group=self.group)
+        uid = t.cpu().numpy()
+        check(be.lib.qfe_comm_init(be.ctx, uid.ctypes.data_as(C.POINTER(C.c_uint8)), self.rank, self.world))
+        be._comm_world = (self.rank, self.world)
+
+    @property
+    def exchanges(self) -> int:
+        if not self.native:
+            return self._exchanges
+        v = C.c_int64()
+        self.backend.lib.qfe_comm_info(self.backend.ctx, None, None, None, C.byref(v), None)
+        return v.value
+
+    @property
+    def exchanged_bytes(self) -> int:
+        if not self.native:
+            return self._exchanged_bytes
+        v = C.c_int64()
+        self.backend.lib.qfe_comm_info(self.backend.ctx, None, None, None, None, C.byref(v))
+        return v.value
+
+    def comm_info(self) -> dict:
+        if not self.native:
+            return {"native": False, "rank": self.rank, "nranks": self.world}
+        r, n, ver = C.c_int(), C.c_int(), C.c_int()
+        self.backend.lib.qfe_comm_info(self.backend.ctx, C.byref(r), C.byref(n), C.byref(ver), None, None)
+        return {"native": True, "rank": r.value, "nranks": n.value, "nccl_version": ver.value}
 
     # ---- plumbing ------------------------------------------------------------------------------
     def plan(self, terms):
@@ -60,8 +119,28 @@ class ShardedEngine:
             self._partner = torch.empty_like(like)
         return self._partner
 
+    def _partner_native(self, like):
+        """Device scratch for the partner shards: two shards when the device has room (the exchange of the next class then overlaps the
+        sweeps of the current one), else one.  Allocated once per shard shape."""
+        import torch
+
+        p = self._partner
+        if p is None or p.dtype != like.dtype or p.device != like.device or p.numel() % like.numel() or p.numel() == 0:
+            self._partner = None
+            free_b = torch.cuda.mem_get_info(like.device)[0]
+            n_buf = 2 if free_b > 2 * like.numel() * like.element_size() + (8 << 30) else 1
+            self._partner = torch.empty(n_buf * like.numel(), dtype=like.dtype, device=like.device)
+        return self._partner
+
+    def _native_args(self, like):
+        from .engine import _dtype_code
+
+        buf = self._partner_native(like)
+        return C.c_void_p(buf.data_ptr()), C.c_int64(buf.numel() * buf.element_size()), _dtype_code(like)
+
     def release_buffers(self) -> None:
         self._partner = None
+        self._work = None
 
     def exchange(self, shard, x_hi: int):
         """Partner shard (rank ^ x_hi) of the vector ``shard`` belongs to; pairwise send/recv."""
@@ -80,13 +159,19 @@ class ShardedEngine:
             req.wait()
         if shard.is_cuda:
             torch.cuda.current_stream(shard.device).synchronize()
-        self.exchanges += 1
-        self.exchanged_bytes += shard.numel() * shard.element_size()
+        self._exchanges += 1
+        self._exchanged_bytes += shard.numel() * shard.element_size()
         return buf
 
     def allreduce(self, values: np.ndarray) -> np.ndarray:
         import torch
 
+        if self.native:
+            from ._lib import as_ptr, check
+
+            v = np.ascontiguousarray(values, dtype=np.float64).copy()
+            check(self.backend.lib.qfe_allreduce_sum(self.backend.ctx, as_ptr(v, C.c_double), v.size))
+            return v
         dist = _dist()
         dev = "cuda" if dist.get_backend(self.group) == "nccl" else "cpu"
         t = torch.from_numpy(np.ascontiguousarray(values, dtype=np.float64)).to(dev)
@@ -99,6 +184,19 @@ class ShardedEngine:
         local class (Engine.expectation_class0_host); the other classes then run on the device copy as in ``expectation``."""
         if plan.terms.n_slots != 1:
             raise ValueError("expectation_host needs a single-operator term set")
+        if self.native:
+            from ._lib import as_ptr, check
+
+            be = self.backend
+            be._check_state(ket_shard, 1 << self.n_local)
+            if shard_host.size != ket_shard.numel() or not shard_host.flags.c_contiguous or shard_host.itemsize != ket_shard.element_size():
+                raise ValueError("host shard must be a contiguous vector of 2^n_local amplitudes of the device buffer's dtype")
+            pp, pb, dt = self._native_args(ket_shard)
+            be._sync_torch()
+            out = np.zeros(2, dtype=np.float64)
+            check(be.lib.qfe_expectation_sharded_host(be.ctx, plan.handle, C.c_void_p(shard_host.ctypes.data), C.c_void_p(ket_shard.data_ptr()), pp, pb, dt,
+                                                      as_ptr(out, C.c_double)))
+            return complex(out[0], out[1])
         local = self.backend.expectation_class0_host(plan, shard_host, ket_shard)
         return self.expectation(plan, ket_shard, _class0=local)
 
@@ -106,6 +204,19 @@ class ShardedEngine:
         """<bra|H|ket> of the whole register (identical on every rank)."""
         bra = ket_shard if bra_shard is None else bra_shard
         n_slots = plan.terms.n_slots
+        if self.native and _class0 is None:
+            from ._lib import as_ptr, check
+
+            be = self.backend
+            be._check_state(ket_shard, 1 << self.n_local)
+            be._check_state(bra, 1 << self.n_local)
+            pp, pb, dt = self._native_args(ket_shard)
+            be._sync_torch()
+            out = np.zeros(2 * n_slots, dtype=np.float64)
+            check(be.lib.qfe_expectation_sharded(be.ctx, plan.handle, C.c_void_p(bra.data_ptr()) if bra_shard is not None else None,
+                                                 C.c_void_p(ket_shard.data_ptr()), pp, pb, dt, as_ptr(out, C.c_double)))
+            vals = out.view(np.complex128)
+            return complex(vals[0]) if n_slots == 1 else vals.copy()
         acc = np.zeros(n_slots, dtype=np.complex128)
         if _class0 is not None:
             acc[0] += _class0  # the local class was evaluated during the upload
@@ -135,6 +246,17 @@ class ShardedEngine:
         import torch
 
         y = torch.empty_like(ket_shard) if out_shard is None else out_shard
+        if self.native:
+            from ._lib import check
+
+            be = self.backend
+            be._check_state(ket_shard, 1 << self.n_local)
+            be._check_state(y, 1 << self.n_local)
+            pp, pb, dt = self._native_args(ket_shard)
+            be._sync_torch()
+            check(be.lib.qfe_apply_sharded(be.ctx, plan.handle, C.c_void_p(ket_shard.data_ptr()), C.c_void_p(y.data_ptr()), pp, pb, dt))
+            be.sync()
+            return y
         first = True
         for x_hi in plan.classes:
             partner = self.exchange(ket_shard, x_hi)
@@ -146,6 +268,20 @@ class ShardedEngine:
 
     def commutator_gradients(self, h_plan, pool_plan, psi_shard, scratch=None) -> np.ndarray:
         """g_k = -i<psi|[H, tau_k]|psi> = 2 Im <H psi|tau_k|psi> (adapt_vqe.py:181-185), sharded."""
+        if self.native:
+            import torch
+
+            from ._lib import as_ptr, check
+
+            be = self.backend
+            be._check_state(psi_shard, 1 << self.n_local)
+            phi = torch.empty_like(psi_shard) if scratch is None else scratch
+            pp, pb, dt = self._native_args(psi_shard)
+            be._sync_torch()
+            g = np.zeros(pool_plan.terms.n_slots, dtype=np.float64)
+            check(be.lib.qfe_commutator_gradients_sharded(be.ctx, h_plan.handle, pool_plan.handle, C.c_void_p(psi_shard.data_ptr()), C.c_void_p(phi.data_ptr()),
+                                                          pp, pb, dt, as_ptr(g, C.c_double)))
+            return g
         phi = self.apply(h_plan, psi_shard, out_shard=scratch)
         vals = np.atleast_1d(self.expectation(pool_plan, psi_shard, bra_shard=phi))
         return 2.0 * vals.imag
@@ -168,6 +304,23 @@ class ShardedEngine:
     def ground_state(self, plan, v0_shard=None, max_iter: int = 300, tol: float = 1e-10, dtype=None, want_vector: bool = True, seed: int = 0):
         """Lanczos on the sharded apply; same recurrence as ``qfe_lanczos`` with the dots all-reduced.
         Returns (E0, psi0 shard or None, info)."""
+        if self.native:
+            import torch
+
+            from ._lib import check
+
+            be = self.backend
+            v = self.random_state(dtype=dtype, seed=seed) if v0_shard is None else v0_shard.clone()
+            be._check_state(v, 1 << self.n_local)
+            if self._work is None or self._work.numel() != 3 * v.numel() or self._work.dtype != v.dtype:
+                self._work = None
+                self._work = torch.empty(3 * v.numel(), dtype=v.dtype, device=v.device)  # kept: no allocation per call, none per iteration
+            pp, pb, dt = self._native_args(v)
+            be._sync_torch()
+            ev, it, res = C.c_double(), C.c_int(), C.c_double()
+            check(be.lib.qfe_lanczos_sharded(be.ctx, plan.handle, C.c_void_p(v.data_ptr()), C.c_void_p(self._work.data_ptr()), pp, pb, max_iter, tol, dt,
+                                             1 if want_vector else 0, C.byref(ev), C.byref(it), C.byref(res)))
+            return ev.value, (v if want_vector else None), {"iterations": it.value, "residual": res.value}
         from scipy.linalg import eigh_tridiagonal
 
         be = self.backend

@@ -64,11 +64,19 @@ t_mat = workloads.hubbard_chain_t(ns)
 hub = qfe.make_hubbard_model(t_mat, 4.0, 2.0)
 hterms = eng.terms_from_integrals(hub.hpq, hub.hpqrs)
 se2 = ShardedEngine(eng, 2 * ns)
-e_s, _, info_s = se2.ground_state(se2.plan(hterms), max_iter=300, tol=1e-10, want_vector=False)
+hplan = se2.plan(hterms)
+e_s, v_s, info_s = se2.ground_state(hplan, max_iter=300, tol=1e-10, want_vector=True)
 e_1, _, info_1 = eng.ground_state(hterms, max_iter=300, tol=1e-10, want_vector=False)
 assert abs(e_s - e_1) <= 1e-9 * abs(e_1), (e_s, e_1)
+# the sharded Ritz vector: unit norm, <v|H|v> = E0, small eigen-residual
+w_s = se2.apply(hplan, v_s)
+eng.axpy(-e_s, v_s, w_s)
+resid = abs(se2.dot(w_s, w_s)) ** 0.5
+assert abs(se2.dot(v_s, v_s) - 1.0) < 1e-10 and abs(se2.expectation(hplan, v_s) - e_s) <= 1e-9 * abs(e_s) and resid <= 1e-4, resid
 if rank == 0:
-    print(f"Lanczos {2 * ns}q Hubbard chain: sharded E0={e_s:.10f} ({info_s['iterations']} it) single E0={e_1:.10f} ({info_1['iterations']} it)", flush=True)
+    print(f"Lanczos {2 * ns}q Hubbard chain: sharded E0={e_s:.10f} ({info_s['iterations']} it, |Hv-Ev|={resid:.1e}) single E0={e_1:.10f} ({info_1['iterations']} it)", flush=True)
+if rank == 0:
+    print("comm:", se.comm_info(), flush=True)
 dist.barrier()
 if rank == 0:
     print("sharded parity ok", flush=True)
