@@ -164,6 +164,11 @@ int qfe_lanczos(qfe_ctx* ctx, const qfe_plan* p, void* v, void* work, int max_it
 int qfe_vec_dot(qfe_ctx* ctx, const void* a, const void* b, int64_t n_amps, int dtype, double out[2]); /* <a|b> */
 int qfe_vec_axpy(qfe_ctx* ctx, const double alpha[2], const void* x, void* y, int64_t n_amps, int dtype); /* y += alpha x */
 int qfe_vec_scale(qfe_ctx* ctx, const double alpha[2], void* x, int64_t n_amps, int dtype);
+/* G[i][j] = <bras[i]|kets[j]> for nb x nk device vectors of n_amps amplitudes (a multiple of 32) in ONE pass per panel of 32 x 32
+ * vectors: out = 2*nb*nk doubles, row-major.  kets = NULL: the Gram matrix of the bras (Hermitian; nk is ignored, out is nb x nb).
+ * bras / kets are HOST arrays of device pointers.  Replaces the per-entry overlap circuits of the natural-gradient optimizer
+ * (qat/fermion/naturalgradient/qfim_plugin.py:159-199) and the dim^2 observables of the subspace expansion (chemistry/qse.py:191-214). */
+int qfe_vec_gram(qfe_ctx* ctx, const void* const* bras, int nb, const void* const* kets, int nk, int64_t n_amps, int dtype, double* out);
 int qfe_vec_fill_random(qfe_ctx* ctx, void* x, int64_t n_amps, int dtype, uint64_t seed, uint64_t offset); /* counter-based N(0,1)+iN(0,1) */
 int qfe_vec_product_state(qfe_ctx* ctx, void* x, int n_local, int shard, int nqbits, const double* alpha_beta /* 4*n doubles */, int dtype);
 /* computational-basis state on a buffer of n_amps amplitudes: all zero, amplitude `index` one (index = -1: all zero; a shard that does
@@ -211,7 +216,8 @@ int qfe_lanczos_sharded(qfe_ctx* ctx, const qfe_plan* p, void* v, void* work, vo
  * P[k] = i^{|x&z|} X^x Z^z (the packed-term convention, coefficient 1).  One call = the reference's
  * make_spin_hamiltonian_trotter_slice(H, coeff) (qat/fermion/trotterisation.py:85-150) with theta[k] = coeff * Re(c_k) in the term
  * order of H, or one layer exp(-i theta_k O_k) of the ADAPT / UCC ansatz (term by term, _grow_ansatz) (qat/plugins/adapt_vqe.py:64-141).  Consecutive rotations
- * whose X masks fit 10 common qubits besides the 3 lowest are fused into one pass over the state.                              */
+ * whose X masks fit 10 common qubits besides the 3 lowest are fused into one pass over the state; a rotation that flips more qubits than that
+ * (long parity-encoding X strings) takes a pass of its own through global memory.                                               */
 int qfe_pauli_rotations(qfe_ctx* ctx, int nqbits, int64_t K, const uint64_t* x, const uint64_t* z, const double* theta, void* psi, int dtype);
 
 #ifdef __cplusplus

@@ -63,6 +63,7 @@ SIGNATURES = {
     "qfe_vec_dot": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, c_double_p]),
     "qfe_vec_axpy": (C.c_int, [C.c_void_p, c_double_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]),
     "qfe_vec_scale": (C.c_int, [C.c_void_p, c_double_p, C.c_void_p, C.c_int64, C.c_int]),
+    "qfe_vec_gram": (C.c_int, [C.c_void_p, c_void_pp, C.c_int, c_void_pp, C.c_int, C.c_int64, C.c_int, c_double_p]),
     "qfe_vec_fill_random": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_uint64, C.c_uint64]),
     "qfe_vec_product_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, c_double_p, C.c_int]),
     "qfe_vec_basis_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int64]),

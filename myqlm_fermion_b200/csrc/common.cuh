@@ -133,6 +133,11 @@ int radix_sort_terms(qfe_ctx* ctx, uint64_t* x, uint64_t* z, uint32_t* owner, ui
 // vals[r] = sum over blocks of partials[r * n_blocks + b] in a fixed order (sweep.cu)
 int reduce_to_vals(qfe_ctx* ctx, const double2* partials, int n_ranges, int n_blocks, double2* vals);
 
+// qfe_expectation_class_part with the option to form only the real part of the value (sweep.cu; used by the sharded driver, whose pair
+// ranks add 2 Re <own|G|partner>)
+int expectation_class_part_impl(qfe_ctx* ctx, const qfe_plan* p, int x_hi, const void* bra, const void* ket, int dtype, int part, int n_parts, bool real_only,
+                                double* out);
+
 // Lanczos recurrence on an abstract operator (lanczos.cu): `apply(cur, w)` enqueues w = H cur on ctx->stream for this rank's part of the
 // vectors (n_amps amplitudes each), `reduce(vals, n)` sums host scalars over the ranks (identity on one GPU).
 struct LanczosOps {

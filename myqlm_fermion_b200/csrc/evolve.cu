@@ -104,6 +104,36 @@ __global__ void __launch_bounds__(EV_NT, 1) rotate_tile_kernel(const __grid_cons
     }
 }
 
+// One rotation whose X mask does not fit a tile (e.g. a parity-encoded hopping term a+_p a_q, whose X string is |p - q| qubits long):
+// one thread per pair (b, b ^ x) with the top X bit of b clear, straight from global memory -- a plain read + write pass.
+struct WideRot {
+    uint64_t x, z;
+    double c, wr, wi;
+    uint32_t kpar;
+};
+
+template <typename real_t>
+__global__ void __launch_bounds__(256) rotate_wide_kernel(typename Cx<real_t>::type* __restrict__ psi, const unsigned long long n_pairs, const WideRot q) {
+    using cplx_t = typename Cx<real_t>::type;
+    const int top = 63 - __clzll((long long)q.x);
+    const unsigned long long lowmask = (1ull << top) - 1ull;
+    const real_t c = (real_t)q.c, wr = (real_t)q.wr, wi = (real_t)q.wi;
+    for (unsigned long long p = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long j = ((p & ~lowmask) << 1) | (p & lowmask);
+        const unsigned long long jp = j ^ q.x;
+        const real_t s = (__popcll(q.z & j) & 1) ? (real_t)-1 : (real_t)1;
+        const real_t sp = q.kpar ? -s : s;
+        const cplx_t u = psi[j], v = psi[jp];
+        cplx_t nu, nv;
+        nu.x = c * u.x + s * (wr * v.x - wi * v.y);
+        nu.y = c * u.y + s * (wr * v.y + wi * v.x);
+        nv.x = c * v.x + sp * (wr * u.x - wi * u.y);
+        nv.y = c * v.y + sp * (wr * u.y + wi * u.x);
+        psi[j] = nu;
+        psi[jp] = nv;
+    }
+}
+
 template <typename real_t>
 __global__ void __launch_bounds__(256) basis_state_kernel(typename Cx<real_t>::type* __restrict__ x, int64_t n, int64_t index) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -152,6 +182,21 @@ int qfe_pauli_rotations(qfe_ctx* ctx, int nqbits, int64_t K, const uint64_t* x, 
     recs.reserve((size_t)K);
     std::vector<EvolveArgs> passes;
     std::vector<int64_t> pass_first;
+    std::vector<WideRot> wide;        // rotations too wide for a tile, each its own pass
+    std::vector<int64_t> pass_wide;   // per pass: index into `wide`, or -1 for a fused tile pass
+    auto rotation_weights = [&](int64_t r, double& c, double& wr, double& wi, uint32_t& kpar) {
+        const int kk = __builtin_popcountll(x[r] & z[r]) & 3;
+        const double sn = std::sin(theta[r]);
+        c = std::cos(theta[r]);
+        // w = -i sin (-i)^k
+        switch (kk) {
+            case 0: wr = 0.0; wi = -sn; break;
+            case 1: wr = -sn; wi = 0.0; break;
+            case 2: wr = 0.0; wi = sn; break;
+            default: wr = sn; wi = 0.0; break;
+        }
+        kpar = (uint32_t)(kk & 1);
+    };
     int64_t i = 0;
     while (i < K) {
         // greedy batch: consecutive rotations whose X masks fit kmax positions together with the 3 low bits
@@ -163,7 +208,21 @@ int qfe_pauli_rotations(qfe_ctx* ctx, int nqbits, int64_t K, const uint64_t* x, 
             L = cand;
             ++j;
         }
-        QFE_REQUIRE(j > i, QFE_ERR_UNSUPPORTED, "qfe_pauli_rotations: rotation %lld flips more than %d qubits", (long long)i, kmax - 3);
+        if (j == i) {
+            // flips more qubits than a tile holds besides the low bits: a pass of its own through global memory
+            WideRot w;
+            w.x = x[i];
+            w.z = z[i];
+            rotation_weights(i, w.c, w.wr, w.wi, w.kpar);
+            EvolveArgs none;
+            memset(&none, 0, sizeof(none));
+            passes.push_back(none);
+            pass_first.push_back((int64_t)recs.size());
+            pass_wide.push_back((int64_t)wide.size());
+            wide.push_back(w);
+            ++i;
+            continue;
+        }
         // pad the tile mask to kmax positions (lowest free positions): larger tiles, fewer of them
         for (int p = 0; p < nqbits && __builtin_popcountll(L) < kmax; ++p) L |= uint64_t(1) << p;
         EvolveArgs a;
@@ -214,28 +273,31 @@ int qfe_pauli_rotations(qfe_ctx* ctx, int nqbits, int64_t K, const uint64_t* x, 
             q.xl = compress(x[r]);
             q.zl = compress(z[r] & L);
             q.zo = z[r] & ~L;
-            const int kk = __builtin_popcountll(x[r] & z[r]) & 3;
-            const double c = std::cos(theta[r]), sn = std::sin(theta[r]);
-            q.c = c;
-            // w = -i sin (-i)^k
-            switch (kk) {
-                case 0: q.wr = 0.0; q.wi = -sn; break;
-                case 1: q.wr = -sn; q.wi = 0.0; break;
-                case 2: q.wr = 0.0; q.wi = sn; break;
-                default: q.wr = sn; q.wi = 0.0; break;
-            }
-            q.kpar = (uint32_t)(kk & 1);
+            rotation_weights(r, q.c, q.wr, q.wi, q.kpar);
             recs.push_back(q);
         }
         a.n_rot = (int)(j - i);
         passes.push_back(a);
+        pass_wide.push_back(-1);
         i = j;
     }
     if (passes.empty()) return QFE_OK;
-    QFE_TRY(ctx->rots.reserve(sizeof(RotRec) * recs.size()));
-    QFE_CUDA(cudaMemcpyAsync(ctx->rots.p, recs.data(), sizeof(RotRec) * recs.size(), cudaMemcpyHostToDevice, ctx->stream));
+    QFE_TRY(ctx->rots.reserve(sizeof(RotRec) * std::max<size_t>(recs.size(), 1)));
+    if (!recs.empty()) QFE_CUDA(cudaMemcpyAsync(ctx->rots.p, recs.data(), sizeof(RotRec) * recs.size(), cudaMemcpyHostToDevice, ctx->stream));
     static int attr_device[2] = {-1, -1};  // per instantiation: the shared-memory opt-in is set once per device
     for (size_t b = 0; b < passes.size(); ++b) {
+        if (pass_wide[b] >= 0) {
+            const WideRot& w = wide[(size_t)pass_wide[b]];
+            const unsigned long long n_pairs = 1ull << (nqbits - 1);
+            const int grid = grid_for((int64_t)n_pairs, 256, ctx->sm_count, 16);
+            if (dtype == QFE_C128)
+                rotate_wide_kernel<double><<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<double2*>(psi), n_pairs, w);
+            else
+                rotate_wide_kernel<float><<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<float2*>(psi), n_pairs, w);
+            ctx->launches++;
+            QFE_CUDA(cudaGetLastError());
+            continue;
+        }
         EvolveArgs& a = passes[b];
         a.rots = ctx->rots.as<RotRec>() + pass_first[b];
         const size_t smem = (elt << a.k) + sizeof(RotRec) * EV_MAX_ROT;

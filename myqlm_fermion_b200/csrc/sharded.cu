@@ -319,7 +319,7 @@ static int expectation_sharded_impl(qfe_ctx* ctx, const qfe_plan* p, const void*
         QFE_TRY(walk.ket_for(ci, &k));
         if (x_hi != 0 && split) {
             const int pivot = __builtin_ctz((unsigned)x_hi);
-            QFE_TRY(qfe_expectation_class_part(ctx, p, x_hi, bra, k, dtype, (ctx->comm_rank >> pivot) & 1, 2, part.data()));
+            QFE_TRY(expectation_class_part_impl(ctx, p, x_hi, bra, k, dtype, (ctx->comm_rank >> pivot) & 1, 2, /*real_only=*/true, part.data()));
             acc[0] += 2.0 * part[0];
         } else {
             QFE_TRY(qfe_expectation_class(ctx, p, x_hi, bra, k, dtype, part.data()));

@@ -349,12 +349,73 @@ __device__ __forceinline__ void times_weight(real_t& sr, real_t& si, const real_
 }
 
 // <own| G |tile> of one group for the thread's 16 rows: sum_r conj(own_r) Wc(r) p_r with p_r the partner of row r.
-template <typename real_t, bool CPLX, int KIND, uint32_t PL>
+// RE_ONLY (real-coefficient sweeps): only the real part of the value is wanted -- the two ranks that hold a pair of shards of a Hermitian
+// class each add 2 Re <own|G|partner> (sharded.cu) -- so only Re conj(own) p (real weights) or Im conj(own) p (imaginary weights) is
+// formed: half of the FP64 work of a full visit.
+template <typename real_t, bool CPLX, int KIND, uint32_t PL, bool RE_ONLY = false>
 __device__ __forceinline__ void group_value_full(const typename CplxOf<real_t>::type* __restrict__ pp, const uint32_t xr, const Terms<real_t, CPLX>& terms,
                                                  const int tb, const int nt, const bool imag, const uint32_t jhi,
                                                  const typename CplxOf<real_t>::type (&own)[R], real_t& out_re, real_t& out_im) {
     using cplx_t = typename CplxOf<real_t>::type;
     (void)xr;
+    if (RE_ONLY && !CPLX) {
+        // Re (Wc sum_r conj(own_r) p_r): Wc = S  ->  S Re(.) ;  Wc = i S  ->  -S Im(.)
+        if (KIND == KIND_FAST) {
+            real_t S, Si;
+            signed_sum_fast<real_t, CPLX>(terms, tb, nt, jhi, S, Si);
+            real_t a0 = (real_t)0, a1 = (real_t)0, a2 = (real_t)0, a3 = (real_t)0;
+            if (!imag) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const cplx_t p = partner_row<(KIND & KIND_XROW) != 0, PL>(pp, xr, r);
+                    if (r & 1) {
+                        a2 = fma(own[r].x, p.x, a2);
+                        a3 = fma(own[r].y, p.y, a3);
+                    } else {
+                        a0 = fma(own[r].x, p.x, a0);
+                        a1 = fma(own[r].y, p.y, a1);
+                    }
+                }
+                out_re = S * ((a0 + a1) + (a2 + a3));
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const cplx_t p = partner_row<(KIND & KIND_XROW) != 0, PL>(pp, xr, r);
+                    if (r & 1) {
+                        a2 = fma(own[r].x, p.y, a2);
+                        a3 = fma(-own[r].y, p.x, a3);
+                    } else {
+                        a0 = fma(own[r].x, p.y, a0);
+                        a1 = fma(-own[r].y, p.x, a1);
+                    }
+                }
+                out_re = -S * ((a0 + a1) + (a2 + a3));
+            }
+        } else {
+            real_t f[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const cplx_t p = partner_row<(KIND & KIND_XROW) != 0, PL>(pp, xr, r);
+                f[r] = imag ? -fma(own[r].x, p.y, -own[r].y * p.x) : fma(own[r].x, p.x, own[r].y * p.y);
+            }
+            int t = tb;
+            const int te = tb + nt;
+            real_t tot = (real_t)0;
+#pragma unroll 1
+            while (t < te) {
+                const uint32_t head = terms.head(t);
+                const uint32_t v = (head >> TZ_V_SHIFT) & 15u;
+                const int len = (int)(head >> TZ_RUN_SHIFT);
+                real_t S, Si;
+                signed_sum<real_t, CPLX, false>(terms, t, t + len, jhi, S, Si);
+                t += len;
+                tot = fma(S, fold_rows<real_t, R>(f, v), tot);
+            }
+            out_re = tot;
+        }
+        out_im = (real_t)0;
+        return;
+    }
     if (KIND == KIND_FAST) {
         real_t Sre, Sim;
         signed_sum_fast<real_t, CPLX>(terms, tb, nt, jhi, Sre, Sim);
@@ -411,7 +472,7 @@ __device__ __forceinline__ void group_value_full(const typename CplxOf<real_t>::
 }
 
 // All groups of one range (same skip bit, polarity and kind) for the thread's 16 rows.
-template <typename real_t, bool CPLX, int MODE, int KIND, uint32_t PL>
+template <typename real_t, bool CPLX, int MODE, int KIND, uint32_t PL, bool RE_ONLY = false>
 __device__ __forceinline__ void process_range(const typename CplxOf<real_t>::type* __restrict__ tile, const Terms<real_t, CPLX>& terms,
                                               const uint2* __restrict__ s_hdr, double2* __restrict__ s_acc_warp, const int g0, const int g1, int tb,
                                               const uint32_t w0, const uint32_t jhi, const bool half,
@@ -471,7 +532,7 @@ __device__ __forceinline__ void process_range(const typename CplxOf<real_t>::typ
             }
         } else if (MODE == MODE_EXPECT || MODE == MODE_BATCH) {
             real_t sr, si;
-            group_value_full<real_t, CPLX, KIND, PL>(pp, xr, terms, tb, nt, imag, jhi, own, sr, si);
+            group_value_full<real_t, CPLX, KIND, PL, RE_ONLY>(pp, xr, terms, tb, nt, imag, jhi, own, sr, si);
             if (MODE == MODE_EXPECT) {
                 e_re += (double)sr;
                 e_im += (double)si;
@@ -898,7 +959,7 @@ template <typename real_t> struct GeoExpect {
 };
 static_assert(GeoExpect<double>::SM_TOTAL <= 232448 - 1024, "exceeds the 227 KB of shared memory a CTA may use");
 
-template <typename real_t, bool PROF>
+template <typename real_t, bool PROF, bool RE_ONLY>
 __global__ void __launch_bounds__(NT_MAX, 1) tile_expect_kernel(const __grid_constant__ SweepArgs a) {
     using G = GeoExpect<real_t>;
     constexpr int NT = NT_MAX, NW = G::NW;
@@ -1014,11 +1075,11 @@ __global__ void __launch_bounds__(NT_MAX, 1) tile_expect_kernel(const __grid_con
                 const int g0 = (int)(d.x & 0xffffu), g1 = (int)(d.x >> 16), t0 = (int)(d.y & 0xffffu);
                 const uint32_t kind = (d.y >> RNG_KIND_SHIFT) & 3u;
                 if (kind == KIND_FAST)
-                    process_range<real_t, false, MODE_EXPECT, KIND_FAST, PLANE>(tile, terms, s_hdr, nullptr, g0, g1, t0, w0, jhi, half, own, acc_re, acc_im, e_re, e_im);
+                    process_range<real_t, false, MODE_EXPECT, KIND_FAST, PLANE, RE_ONLY>(tile, terms, s_hdr, nullptr, g0, g1, t0, w0, jhi, half, own, acc_re, acc_im, e_re, e_im);
                 else if (kind == KIND_RUNS)
-                    process_range<real_t, false, MODE_EXPECT, KIND_RUNS, PLANE>(tile, terms, s_hdr, nullptr, g0, g1, t0, w0, jhi, half, own, acc_re, acc_im, e_re, e_im);
+                    process_range<real_t, false, MODE_EXPECT, KIND_RUNS, PLANE, RE_ONLY>(tile, terms, s_hdr, nullptr, g0, g1, t0, w0, jhi, half, own, acc_re, acc_im, e_re, e_im);
                 else
-                    process_range<real_t, false, MODE_EXPECT, KIND_RUNS | KIND_XROW, PLANE>(tile, terms, s_hdr, nullptr, g0, g1, t0, w0, jhi, half, own, acc_re, acc_im, e_re, e_im);
+                    process_range<real_t, false, MODE_EXPECT, KIND_RUNS | KIND_XROW, PLANE, RE_ONLY>(tile, terms, s_hdr, nullptr, g0, g1, t0, w0, jhi, half, own, acc_re, acc_im, e_re, e_im);
             }
         }
         if (PROF && (tid & 31) == 0) {
@@ -1038,6 +1099,126 @@ __global__ void __launch_bounds__(NT_MAX, 1) tile_expect_kernel(const __grid_con
     if (PROF && a.prof) {
         __syncthreads();
         if (tid < NW * PROF_PHASES) atomicAdd(a.prof + tid, s_prof[tid]);
+    }
+}
+
+// ---- pipelined APPLY kernel --------------------------------------------------------------------------------------------------------
+// y (+)= H|ket> for real-coefficient sweeps over full tiles: the group loops and the write-back through the tile of tile_sweep_kernel
+// <APPLY>, with the tile switch of tile_expect_kernel -- the next ket tile is requested as soon as the accumulators have left the
+// registers (before the read-modify-write of y, which then overlaps those loads), tile offsets come from tables.
+template <typename real_t>
+__global__ void __launch_bounds__(NT_MAX, 1) tile_apply_kernel(const __grid_constant__ SweepArgs a) {
+    using G = GeoExpect<real_t>;
+    constexpr int NT = NT_MAX;
+    constexpr uint32_t PLANE = G::PLANE;
+    using cplx_t = typename CplxOf<real_t>::type;
+    extern __shared__ __align__(16) unsigned char smem[];
+    cplx_t* const tile = reinterpret_cast<cplx_t*>(smem + G::SM_TILE);
+    uint2* s_hdr = reinterpret_cast<uint2*>(smem + G::SM_HDR);
+    uint2* s_rng = reinterpret_cast<uint2*>(smem + G::SM_RNG);
+    uint64_t* s_nat_off = reinterpret_cast<uint64_t*>(smem + G::SM_NATOFF);
+    uint64_t* s_base = reinterpret_cast<uint64_t*>(smem + G::SM_BASE);
+    uint32_t* s_nat_loc = reinterpret_cast<uint32_t*>(smem + G::SM_NATLOC);
+
+    const int nG = a.n_groups, nR = a.n_ranges;
+    const int tid = threadIdx.x;
+    const cplx_t* __restrict__ ket = reinterpret_cast<const cplx_t*>(a.ket);
+    cplx_t* __restrict__ yout = reinterpret_cast<cplx_t*>(a.out_vec);
+
+    for (int g = tid; g < nG; g += NT) s_hdr[g] = make_uint2(a.g_hdr[2 * g], a.g_hdr[2 * g + 1]);
+    for (int g = tid; g < nR; g += NT) s_rng[g] = make_uint2(a.r_desc[2 * g], a.r_desc[2 * g + 1]);
+    for (int i = tid; i < PLAN_TABLE; i += NT) {
+        s_nat_off[i] = a.nat_off[i];
+        s_nat_loc[i] = a.nat_loc[i];
+    }
+    {
+        unsigned long long rest = (unsigned long long)(tid & 127) << (7 * (tid >> 7));
+        uint64_t b = 0;
+        for (int r = 0; r < a.n_runs; ++r) {
+            const int len = a.run_len[r];
+            b |= (rest & ((1ull << len) - 1ull)) << a.run_pos[r];
+            rest >>= len;
+        }
+        s_base[tid] = b;
+    }
+    __syncthreads();
+
+    const uint32_t jhi = (uint32_t)tid << RB, w0 = (uint32_t)tid;
+    auto base_of = [&](const unsigned long long t) {
+        return s_base[t & 127] | s_base[128 + ((t >> 7) & 127)] | s_base[256 + ((t >> 14) & 127)] | s_base[384 + ((t >> 21) & 127)];
+    };
+    const uint64_t off_lo = s_nat_off[tid & 127];
+    const uint32_t loc_lo = s_nat_loc[tid & 127];
+    cplx_t v[R];
+    auto request = [&](const unsigned long long t) {
+        const uint64_t kb = (base_of(t) ^ a.ket_xor) | off_lo;
+#pragma unroll
+        for (int u = 0; u < R; ++u) v[u] = ld_stream(ket + (kb | s_nat_off[128 + ((tid + u * NT) >> 7)]));
+    };
+
+    unsigned long long tile_id = a.tile_begin + blockIdx.x;
+    if (tile_id < a.n_tiles) request(tile_id);
+    for (; tile_id < a.n_tiles; tile_id += a.tile_stride) {
+        const unsigned long long next_id = tile_id + a.tile_stride;
+        const uint64_t ybase = base_of(tile_id) | off_lo;
+        __syncthreads();  // the write-back of the previous tile has read the tile
+#pragma unroll
+        for (int u = 0; u < R; ++u) tile[tile_word<PLANE>(loc_lo | s_nat_loc[128 + ((tid + u * NT) >> 7)])] = v[u];
+        __syncthreads();
+        // y += ...: the tile's lines of y travel to L2 while the groups are processed, for the read-modify-write that ends the tile
+        if (a.accumulate && a.prefetch_dist > 0)
+#pragma unroll
+            for (uint32_t idx = 8u * tid; idx < (uint32_t)(R * NT); idx += 8u * NT)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(yout + (base_of(tile_id) | s_nat_off[idx & 127] | s_nat_off[128 + (idx >> 7)])));
+        {
+            real_t acc_re[R], acc_im[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) acc_re[r] = acc_im[r] = (real_t)0;
+            cplx_t own[R];  // EXPECT / BATCH only: unused here
+            double e_re = 0.0, e_im = 0.0;
+            const Terms<real_t, false> terms{a, (uint32_t)tile_id};
+#pragma unroll 1
+            for (int ri = 0; ri < nR; ++ri) {
+                const uint2 d = s_rng[ri];
+                const int g0 = (int)(d.x & 0xffffu), g1 = (int)(d.x >> 16), t0 = (int)(d.y & 0xffffu);
+                const uint32_t kind = (d.y >> RNG_KIND_SHIFT) & 3u;
+                if (kind == KIND_FAST)
+                    process_range<real_t, false, MODE_APPLY, KIND_FAST, PLANE>(tile, terms, s_hdr, nullptr, g0, g1, t0, w0, jhi, false, own, acc_re, acc_im, e_re, e_im);
+                else if (kind == KIND_RUNS)
+                    process_range<real_t, false, MODE_APPLY, KIND_RUNS, PLANE>(tile, terms, s_hdr, nullptr, g0, g1, t0, w0, jhi, false, own, acc_re, acc_im, e_re, e_im);
+                else
+                    process_range<real_t, false, MODE_APPLY, KIND_RUNS | KIND_XROW, PLANE>(tile, terms, s_hdr, nullptr, g0, g1, t0, w0, jhi, false, own, acc_re, acc_im, e_re, e_im);
+            }
+            __syncthreads();  // every partner row has been read: the result leaves through the tile
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                cplx_t o;
+                o.x = acc_re[r];
+                o.y = acc_im[r];
+                tile[(uint32_t)r * PLANE + w0] = o;
+            }
+        }
+        // the accumulators are in the tile: their registers take the next ket tile, which travels during the write-back
+        request(next_id < a.n_tiles ? next_id : tile_id);
+        __syncthreads();
+        // natural order: y is read and written in 128 B contiguous segments, 8 independent loads in flight per thread
+#pragma unroll
+        for (int h = 0; h < R; h += R / 2) {
+            cplx_t yv[R / 2];
+            if (a.accumulate) {
+#pragma unroll
+                for (int u = 0; u < R / 2; ++u) yv[u] = yout[ybase | s_nat_off[128 + ((tid + (h + u) * NT) >> 7)]];
+            }
+#pragma unroll
+            for (int u = 0; u < R / 2; ++u) {
+                cplx_t o = tile[tile_word<PLANE>(loc_lo | s_nat_loc[128 + ((tid + (h + u) * NT) >> 7)])];
+                if (a.accumulate) {
+                    o.x += yv[u].x;
+                    o.y += yv[u].y;
+                }
+                yout[ybase | s_nat_off[128 + ((tid + (h + u) * NT) >> 7)]] = o;
+            }
+        }
     }
 }
 
@@ -1229,9 +1410,9 @@ static bool prof_enabled() {
     return on;
 }
 
-template <typename real_t, bool PROF>
+template <typename real_t, bool PROF, bool RE_ONLY>
 static int launch_expect_pipelined_p(qfe_ctx* ctx, SweepArgs& args, int grid) {
-    auto kern = tile_expect_kernel<real_t, PROF>;
+    auto kern = tile_expect_kernel<real_t, PROF, RE_ONLY>;
     constexpr size_t smem = GeoExpect<real_t>::SM_TOTAL;
     static int attr_device = -1;
     if (attr_device != ctx->device) {
@@ -1259,12 +1440,33 @@ static bool pipelined_eligible(const SweepArgs& args, bool cplx) {
     static const bool on = env_flag("QFE_PIPELINED", true);
     return on && !cplx && args.k == PLAN_MAX_TILE_BITS && args.split == 1;
 }
-static int launch_expect_pipelined(qfe_ctx* ctx, SweepArgs& args, int grid, int dtype) {
+static int launch_expect_pipelined(qfe_ctx* ctx, SweepArgs& args, int grid, int dtype, bool real_only) {
     if (prof_enabled()) {
         QFE_TRY(prof_buffer(ctx, args));
-        return dtype == QFE_C128 ? launch_expect_pipelined_p<double, true>(ctx, args, grid) : launch_expect_pipelined_p<float, true>(ctx, args, grid);
+        return dtype == QFE_C128 ? launch_expect_pipelined_p<double, true, false>(ctx, args, grid) : launch_expect_pipelined_p<float, true, false>(ctx, args, grid);
     }
-    return dtype == QFE_C128 ? launch_expect_pipelined_p<double, false>(ctx, args, grid) : launch_expect_pipelined_p<float, false>(ctx, args, grid);
+    if (real_only && !args.same_tile)  // (on the state's own tile the Hermitian half visit already forms the real part only)
+        return dtype == QFE_C128 ? launch_expect_pipelined_p<double, false, true>(ctx, args, grid) : launch_expect_pipelined_p<float, false, true>(ctx, args, grid);
+    return dtype == QFE_C128 ? launch_expect_pipelined_p<double, false, false>(ctx, args, grid) : launch_expect_pipelined_p<float, false, false>(ctx, args, grid);
+}
+
+template <typename real_t>
+static int launch_apply_pipelined_t(qfe_ctx* ctx, SweepArgs& args, int grid) {
+    auto kern = tile_apply_kernel<real_t>;
+    constexpr size_t smem = GeoExpect<real_t>::SM_TOTAL;
+    static int attr_device = -1;
+    if (attr_device != ctx->device) {
+        QFE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_device = ctx->device;
+    }
+    args.tile_stride = (unsigned long long)grid;
+    kern<<<grid, NT_MAX, smem, ctx->stream>>>(args);
+    ctx->launches++;
+    QFE_CUDA(cudaGetLastError());
+    return QFE_OK;
+}
+static int launch_apply_pipelined(qfe_ctx* ctx, SweepArgs& args, int grid, int dtype) {
+    return dtype == QFE_C128 ? launch_apply_pipelined_t<double>(ctx, args, grid) : launch_apply_pipelined_t<float>(ctx, args, grid);
 }
 
 template <typename real_t, bool CPLX, int MODE>
@@ -1378,7 +1580,7 @@ struct UploadPipe {
 };
 
 static int run_class_reduce(qfe_ctx* ctx, const qfe_plan* p, int ci, const void* bra, const void* ket, int dtype, int part, int n_parts,
-                            std::vector<double>& host_vals, std::vector<int32_t>& val_slot, const UploadPipe* pipe = nullptr) {
+                            std::vector<double>& host_vals, std::vector<int32_t>& val_slot, const UploadPipe* pipe = nullptr, bool real_only = false) {
     const ClassHost& cls = p->h.classes[ci];
     const bool batch = p->batch;
     const bool tiles = p->h.use_tiles && !p->force_direct;
@@ -1440,7 +1642,7 @@ static int run_class_reduce(qfe_ctx* ctx, const qfe_plan* p, int ci, const void*
             if (batch)
                 QFE_TRY(launch_tile_d<MODE_BATCH>(ctx, a, grid, sw.complex_w, dtype));
             else if (pipelined_eligible(a, sw.complex_w))
-                QFE_TRY(launch_expect_pipelined(ctx, a, grid, dtype));
+                QFE_TRY(launch_expect_pipelined(ctx, a, grid, dtype, real_only));
             else
                 QFE_TRY(launch_tile_d<MODE_EXPECT>(ctx, a, grid, sw.complex_w, dtype));
             for (int g = 0; g < n_ranges; ++g) val_slot.push_back(batch ? p->h.g_slot[sw.group_begin + g] : 0);
@@ -1639,6 +1841,15 @@ int qfe_expectation_class(qfe_ctx* ctx, const qfe_plan* p, int x_hi, const void*
 }
 
 int qfe_expectation_class_part(qfe_ctx* ctx, const qfe_plan* p, int x_hi, const void* bra, const void* ket, int dtype, int part, int n_parts, double* out) {
+    return expectation_class_part_impl(ctx, p, x_hi, bra, ket, dtype, part, n_parts, false, out);
+}
+
+}  // extern "C"
+
+namespace qfe {
+// real_only: the caller uses the real part of the result only (imaginary parts come back as computed or as zero)
+int expectation_class_part_impl(qfe_ctx* ctx, const qfe_plan* p, int x_hi, const void* bra, const void* ket, int dtype, int part, int n_parts, bool real_only,
+                                double* out) {
     QFE_REQUIRE(ctx && p && bra && ket && out, QFE_ERR_ARG, "qfe_expectation_class: null argument");
     QFE_REQUIRE(dtype == QFE_C128 || dtype == QFE_C64, QFE_ERR_ARG, "unknown dtype %d", dtype);
     QFE_REQUIRE(n_parts >= 1 && part >= 0 && part < n_parts, QFE_ERR_ARG, "qfe_expectation_class_part: part %d of %d", part, n_parts);
@@ -1648,13 +1859,16 @@ int qfe_expectation_class_part(qfe_ctx* ctx, const qfe_plan* p, int x_hi, const 
     if (ci < 0) return QFE_OK;  // no term flips these high qubits
     std::vector<double> vals;
     std::vector<int32_t> slots;
-    QFE_TRY(run_class_reduce(ctx, p, ci, bra, ket, dtype, part, n_parts, vals, slots));
+    QFE_TRY(run_class_reduce(ctx, p, ci, bra, ket, dtype, part, n_parts, vals, slots, nullptr, real_only));
     for (size_t i = 0; i < slots.size(); ++i) {
         out[2 * slots[i]] += vals[2 * i];
         out[2 * slots[i] + 1] += vals[2 * i + 1];
     }
     return QFE_OK;
 }
+}  // namespace qfe
+
+extern "C" {
 
 int qfe_expectation(qfe_ctx* ctx, const qfe_plan* p, const void* psi, int dtype, double out[2]) {
     QFE_REQUIRE(ctx && p && psi && out, QFE_ERR_ARG, "qfe_expectation: null argument");
@@ -1786,7 +2000,10 @@ int qfe_apply_class(qfe_ctx* ctx, const qfe_plan* p, int x_hi, const void* ket, 
                 a.out_vec = y;
                 a.accumulate = (si == cls.sweep_begin) ? (accumulate ? 1 : 0) : 1;
             }
-            QFE_TRY(launch_tile_d<MODE_APPLY>(ctx, a, sweep_grid(ctx, sw, split), sw.complex_w, dtype));
+            if (pipelined_eligible(a, sw.complex_w))
+                QFE_TRY(launch_apply_pipelined(ctx, a, sweep_grid(ctx, sw, split), dtype));
+            else
+                QFE_TRY(launch_tile_d<MODE_APPLY>(ctx, a, sweep_grid(ctx, sw, split), sw.complex_w, dtype));
         }
         if (split > 1) {
             const int64_t n_amps = int64_t(1) << p->h.n_local;

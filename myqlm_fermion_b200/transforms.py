@@ -93,17 +93,22 @@ def _fenwick_parents(n: int):
     return parent
 
 
-def make_PCU_sets(j: int, nqbits: int):
-    """(P, C, U) qubit sets of mode j (transforms.py:67-79)."""
-    parent = _fenwick_parents(nqbits)
+def _pcu_of_mode(j: int, parent) -> tuple:
     anc = []
     a = parent[j]
     while a >= 0:
         anc.append(a)
         a = parent[a]
-    children = {k for k in range(nqbits) if parent[k] == j}
+    children = {k for k in range(len(parent)) if parent[k] == j}
     c_set = {k for k in range(j) if parent[k] in anc}
     return c_set | children, c_set, set(anc)
+
+
+def make_PCU_sets(nqbits: int) -> list:
+    """[(P, C, U)] qubit sets of every mode 0..nqbits-1, the reference's signature and return value (transforms.py:65-79); the
+    Fenwick tree is built once."""
+    parent = _fenwick_parents(nqbits)
+    return [_pcu_of_mode(j, parent) for j in range(nqbits)]
 
 
 def get_jw_code(nbits: int) -> np.ndarray:

@@ -151,6 +151,17 @@ def test_transforms_match_the_recoded_fock_matrix(transform, code):
 
 
 # ---- normal ordering (test_unitary_fermion_algebra.py) -------------------------------------------------------------------------
+def test_make_pcu_sets_keeps_the_reference_signature():
+    """make_PCU_sets(nqbits) -> [(P, C, U)] for every qubit (/root/reference/qat/fermion/transforms.py:65-79); the known answers are
+    SURVEY.md appendix A's probe vectors, the same ones the oracle is pinned to."""
+    from myqlm_fermion_b200 import make_PCU_sets
+
+    assert make_PCU_sets(5) == [(set(), set(), {1, 2, 4}), ({0}, set(), {2, 4}), ({1}, set(), {4}), ({2}, {2}, {4}), ({2, 3}, set(), set())]
+    got8 = make_PCU_sets(8)
+    assert len(got8) == 8 and got8[6] == ({3, 5}, {3, 5}, {7}) and got8[7] == ({3, 5, 6}, set(), set())
+    assert make_PCU_sets(1) == [(set(), set(), set())]
+
+
 def test_normal_ordering_of_single_terms():
     from myqlm_fermion_b200 import FermionicTerm, normal_order_fermionic_term
 

@@ -70,12 +70,42 @@ def test_random_rotations_match_the_oracle(eng, n):
     assert np.max(np.abs(d32.cpu().numpy() - want)) <= RTOL32 * np.max(np.abs(want)) * 10
 
 
+@pytest.mark.parametrize("n", [15, 17])
+def test_wide_rotations_take_the_direct_pass(eng, n):
+    """Rotations that flip more qubits than a tile holds (ADVICE r1: a parity-encoded a+_p a_q carries an X string of length |p - q|;
+    the reference's _grow_ansatz / make_spin_hamiltonian_trotter_slice have no width limit): unrestricted random X masks, the full
+    register, and a parity-encoded long-range excitation, interleaved with narrow rotations so that the order is exercised."""
+    rng = np.random.default_rng(100 + n)
+    K = 24
+    x = rng.integers(0, 1 << n, size=K, dtype=np.uint64)  # ~n/2 flipped qubits each: most do not fit a tile
+    x[3] = np.uint64((1 << n) - 1)
+    x[5] = np.uint64(1)
+    x[9] = np.uint64(0)
+    z = rng.integers(0, 1 << n, size=K, dtype=np.uint64)
+    theta = rng.uniform(-np.pi, np.pi, size=K)
+    psi = _state(n, 3)
+    want = evolve.rotations(n, x, z, theta, psi)
+    d = _dev(psi)
+    eng.pauli_rotations(d, x, z, theta)
+    assert np.max(np.abs(d.cpu().numpy() - want)) <= RTOL64 * np.max(np.abs(want))
+    d32 = _dev(psi.astype(np.complex64))
+    eng.pauli_rotations(d32, x, z, theta)
+    assert np.max(np.abs(d32.cpu().numpy() - want)) <= RTOL32 * np.max(np.abs(want)) * 10
+    # i (a+_1 a_{n-2} - h.c.) in the parity encoding: every term flips qubits 1 .. n-2
+    op = transforms.transform(n, [(1j, "Cc", [1, n - 2]), (-1j, "Cc", [n - 2, 1])], 0.0, "parity")
+    xs, zs, cs, _ = op.canonical()
+    assert min(bin(int(v)).count("1") for v in xs) >= n - 3 > 10
+    th = 0.37 * np.real(cs)
+    want = evolve.rotations(n, xs, zs, th, psi)
+    d = _dev(psi)
+    eng.pauli_rotations(d, xs, zs, th)
+    assert np.max(np.abs(d.cpu().numpy() - want)) <= RTOL64 * np.max(np.abs(want))
+
+
 def test_rotation_argument_errors(eng):
     import myqlm_fermion_b200 as qfe
 
     d = _dev(_state(15, 0))
-    with pytest.raises(qfe.QfeError):  # flips 14 qubits: wider than a tile
-        eng.pauli_rotations(d, [(1 << 14) - 1 << 1], [0], [0.1])
     with pytest.raises(qfe.QfeError):  # acts outside the register
         eng.pauli_rotations(d, [1 << 20], [0], [0.1])
     with pytest.raises(ValueError):
@@ -163,6 +193,26 @@ def test_gram_qfim_and_energy_gradient(eng):
     want_grad = np.array([2 * np.vdot(s, phi).real for s in states])
     got_grad = eng.energy_gradient(terms, d_states, d_psi)
     assert np.max(np.abs(got_grad - want_grad)) <= RTOL64 * np.max(np.abs(want_grad))
+
+
+@pytest.mark.parametrize("n,nb,nk", [(5, 3, 2), (10, 5, 3), (12, 40, 0), (11, 33, 35), (4, 2, 2)])
+def test_batched_gram_kernel(eng, n, nb, nk):
+    """qfe_vec_gram: G[i, j] = <b_i|k_j> in one pass per 32 x 32 panel, against numpy; nk = 0 stands for the Hermitian Gram matrix of
+    the bras.  Panel edges (33, 35, 40 vectors), registers below the 32-amplitude chunk (n = 4) and complex64 included."""
+    rng = np.random.default_rng(n * 100 + nb)
+    B = rng.standard_normal((nb, 1 << n)) + 1j * rng.standard_normal((nb, 1 << n))
+    Kk = B if nk == 0 else rng.standard_normal((nk, 1 << n)) + 1j * rng.standard_normal((nk, 1 << n))
+    want = np.conj(B) @ Kk.T
+    db = [_dev(v) for v in B]
+    dk = None if nk == 0 else [_dev(v) for v in Kk]
+    got = eng.gram(db, dk)
+    assert got.shape == want.shape and np.max(np.abs(got - want)) <= RTOL64 * np.max(np.abs(want))
+    if nk == 0:
+        assert np.array_equal(got, np.conj(got.T))  # mirrored, not recomputed
+    B32, K32 = B.astype(np.complex64), Kk.astype(np.complex64)
+    got32 = eng.gram([_dev(v) for v in B32], None if nk == 0 else [_dev(v) for v in K32])
+    want32 = np.conj(B32.astype(np.complex128)) @ K32.astype(np.complex128).T
+    assert np.max(np.abs(got32 - want32)) <= RTOL64 * np.max(np.abs(want32))  # complex64 inputs, double accumulation
 
 
 def test_qse_matrices(eng):

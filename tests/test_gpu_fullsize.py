@@ -9,6 +9,9 @@
 
 Runs on the B200 (-m gpu); about two minutes."""
 
+import json
+from pathlib import Path
+
 import numpy as np
 import pytest
 
@@ -25,8 +28,12 @@ def eng():
 
 
 def _free_gb():
+    import gc
+
     import torch
 
+    gc.collect()
+    torch.cuda.empty_cache()  # earlier tests' vectors sit in torch's caching allocator
     return torch.cuda.mem_get_info(0)[0] / 2**30
 
 
@@ -73,6 +80,30 @@ def test_config4_product_and_basis_state_energies_at_32_qubits(eng):
     assert abs(got_b - want_b) <= RTOL64 * abs(want_b), (got_b, want_b)
 
 
+def test_config4_random_state_energy_is_real_and_equals_psi_dot_hpsi_at_32_qubits(eng):
+    """SURVEY.md 8d (iii) at full size: <psi|H|psi> of a random 32-qubit state is real and equals <psi|(H psi)> from the apply path
+    (a different kernel mode: full visits, write-back through the tile).  Two 68.7 GB vectors."""
+    import torch
+
+    from myqlm_fermion_b200 import workloads
+
+    n = 32
+    if _free_gb() < 150:
+        pytest.skip("needs two 32-qubit complex128 vectors (137 GB)")
+    hpq, hpqrs = workloads.synthetic_h_integrals(n // 2, seed=1234)
+    terms = eng.terms_from_integrals(hpq, hpqrs, constant=0.25)
+    del hpqrs
+    plan = eng.plan(terms)
+    psi = eng.random_state(n, seed=0)
+    e = eng.expectation(plan, psi)
+    assert abs(e.imag) <= 1e-12 * abs(e), e
+    phi = eng.apply(plan, psi)
+    e2 = eng.dot(psi, phi)
+    assert abs(e2 - e) <= RTOL64 * abs(e), (e, e2)
+    del psi, phi
+    torch.cuda.empty_cache()
+
+
 def test_config3_hubbard_chain_24_qubits_lanczos(eng):
     import torch
 
@@ -82,7 +113,12 @@ def test_config3_hubbard_chain_24_qubits_lanczos(eng):
     hs = make_hubbard_model(workloads.hubbard_chain_t(ns), 4.0, 2.0).to_spin("jordan-wigner")
     terms = hs.packed(eng)
     assert terms.n_terms == 56  # T = 57 with the identity
+    # the reference's own route, precomputed on the CPU by tests/golden/make_golden_lanczos.py: eigsh(get_matrix(sparse=True), which="SA")
+    # (tests/integration/test_integration_models.py:102-103) on the oracle's 24-qubit matrix
+    golden = json.loads((Path(__file__).parent / "golden" / "hubbard_chain_24q_eigsh.json").read_text())
+    assert golden["n_qubits"] == 24 and golden["pauli_terms"] == 56
     e0, psi0, info = eng.ground_state(terms, max_iter=600, tol=1e-11)
+    assert abs(e0 - golden["e0"]) <= RTOL64 * abs(golden["e0"]), (e0, golden["e0"], info)
     phi = eng.apply(terms, psi0)
     e = eng.expectation(terms, psi0)
     assert abs(e.imag) <= 1e-12 * abs(e) and abs(e.real - e0) <= RTOL64 * abs(e0)
@@ -91,7 +127,7 @@ def test_config3_hubbard_chain_24_qubits_lanczos(eng):
     assert abs(eng.dot(phi, phi)) ** 0.5 <= 2e-5, info  # eigen-residual
     assert abs(eng.dot(psi0, psi0) - 1.0) < 1e-10
     e32, _, _ = eng.ground_state(terms, max_iter=600, tol=1e-6, dtype=torch.complex64)
-    assert abs(e32 - e0) <= RTOL32 * abs(e0)
+    assert abs(e32 - golden["e0"]) <= RTOL32 * abs(golden["e0"])
 
 
 def test_config5_pool_gradients_at_26_qubits(eng):

@@ -1,5 +1,5 @@
-"""Parity of the pipelined EXPECT kernel (csrc/sweep.cu:tile_expect_kernel: next tile requested before the barrier, table-driven tile
-offsets) against the oracle at sizes the oracle finishes in seconds.  The kernel is the default for real-coefficient sweeps over full tiles when every SM
+"""Parity of the pipelined EXPECT and APPLY kernels (csrc/sweep.cu:tile_expect_kernel, tile_apply_kernel: next tile requested before the
+barrier, table-driven tile offsets) against the oracle at sizes the oracle finishes in seconds.  The kernel is the default for real-coefficient sweeps over full tiles when every SM
 has its own tile (>= 20 qubits); QFE_SPLIT=1 makes small registers take the same path, so the check runs in a child process with that
 knob and with QFE_PROF=1, whose counters prove which kernel ran.  Tolerances: BASELINE.json (1e-10 complex128, 1e-5 complex64)."""
 
@@ -47,9 +47,18 @@ for m, enc in [(7, "jordan-wigner"), (7, "bravyi-kitaev"), (7, "parity"), (8, "j
     t = eng.expectation(plan, dev(psi), bra=dev(bra))
     psi32 = psi.astype(np.complex64)
     e32 = eng.expectation(plan, dev(psi32))
+    l0 = eng.launch_count()
+    phi_dev = eng.apply(plan, dev(psi)).cpu().numpy()        # pipelined APPLY kernel (tile_apply_kernel): unsplit full tiles
+    apply_launches = eng.launch_count() - l0
+    phi_acc = dev(psi.copy())                                 # y += H psi on a non-zero y: two applies of the same plan through apply_class
+    eng.apply_class(plan, 0, dev(psi), phi_acc, accumulate=True)
+    phi32 = eng.apply(plan, dev(psi32)).cpu().numpy()
     want32 = np.vdot(psi32.astype(np.complex128), spin.apply_packed(n, x, z, c, complex(k[0]), psi32.astype(np.complex128)))
     out.append(dict(m=m, enc=enc, tile_bits=plan.tile_bits, async_tiles=tiles, e=[e.real, e.imag], want_e=[np.vdot(psi, phi).real, np.vdot(psi, phi).imag],
-                    t=[t.real, t.imag], want_t=[np.vdot(bra, phi).real, np.vdot(bra, phi).imag], e32=[e32.real, e32.imag], want32=[want32.real, want32.imag]))
+                    t=[t.real, t.imag], want_t=[np.vdot(bra, phi).real, np.vdot(bra, phi).imag], e32=[e32.real, e32.imag], want32=[want32.real, want32.imag],
+                    apply_dev=float(np.max(np.abs(phi_dev - phi)) / np.max(np.abs(phi))), apply_launches=apply_launches, sweeps=plan.n_sweeps,
+                    apply_acc_dev=float(np.max(np.abs(phi_acc.cpu().numpy() - (psi + phi))) / np.max(np.abs(phi))),
+                    apply32_dev=float(np.max(np.abs(phi32 - phi)) / np.max(np.abs(phi)))))
 print("RESULT " + json.dumps(out))
 """
 
@@ -68,3 +77,5 @@ def test_pipelined_expect_kernel_matches_the_oracle():
         assert abs(t - w) <= 1e-10 * max(abs(w), 1e-3), row
         e, w = complex(*row["e32"]), complex(*row["want32"])
         assert abs(e - w) <= 1e-5 * abs(w), row
+        assert row["apply_launches"] == row["sweeps"], row  # one launch per sweep: no slab combine, i.e. the unsplit path ran
+        assert row["apply_dev"] <= 1e-10 and row["apply_acc_dev"] <= 1e-10 and row["apply32_dev"] <= 1e-4, row

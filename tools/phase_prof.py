@@ -16,6 +16,7 @@ from myqlm_fermion_b200.workloads import synthetic_h_integrals
 
 m = int(sys.argv[1]) if len(sys.argv) > 1 else 14
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+transition = "transition" in sys.argv[3:]  # <phi|H|psi> with phi != psi: the path of the non-local classes (bra tile != ket tile, full visits)
 n = 2 * m
 eng = qfe.get_engine(0)
 eng.use_torch_stream()
@@ -23,19 +24,20 @@ hpq, hpqrs = synthetic_h_integrals(m, seed=1234)
 terms = eng.terms_from_integrals(hpq, hpqrs)
 plan = eng.plan(terms)
 psi = eng.random_state(n, dtype=torch.complex128, seed=0)
-e = eng.expectation(plan, psi)  # warm-up
+bra = eng.random_state(n, dtype=torch.complex128, seed=1) if transition else None
+e = eng.expectation(plan, psi, bra=bra)  # warm-up
 cyc = np.zeros(16 * 8, dtype=np.uint64)
 eng.lib.qfe_dev_phase_cycles(eng.ctx, cyc.ctypes.data_as(C.POINTER(C.c_uint64)), 1)
 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 torch.cuda.synchronize()
 ev0.record()
 for _ in range(reps):
-    e = eng.expectation(plan, psi)
+    e = eng.expectation(plan, psi, bra=bra)
 ev1.record()
 torch.cuda.synchronize()
 ms = ev0.elapsed_time(ev1) / reps
 eng.lib.qfe_dev_phase_cycles(eng.ctx, cyc.ctypes.data_as(C.POINTER(C.c_uint64)), 1)
-out = {"n": n, "terms": terms.n_terms, "sweeps": plan.n_sweeps, "env": {k: v for k, v in os.environ.items() if k.startswith("QFE_")},
+out = {"transition": transition, "n": n, "terms": terms.n_terms, "sweeps": plan.n_sweeps, "env": {k: v for k, v in os.environ.items() if k.startswith("QFE_")},
        "ms": ms, "terms_amps_per_s": terms.n_terms * float(1 << n) / (ms / 1e3), "energy": e.real}
 if cyc.any():
     c = cyc.reshape(16, 8).astype(np.float64)
