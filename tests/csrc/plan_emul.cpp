@@ -225,15 +225,15 @@ extern "C" int plan_emul_dump(int n, int64_t T, const uint64_t* x, const uint64_
     if (build_plan(v, n_local, shard, lim, p, &err) != 0) return 1;
     FILE* f = fopen(path, "w");
     if (!f) return 2;
-    fprintf(f, "sweep,range,kind,skipbit,pol,group,nt,xword,imag,tile_mask\n");
+    fprintf(f, "sweep,range,kind,skipbit,pol,group,nt,xword,imag,tile_mask,x_hi\n");
     for (size_t si = 0; si < p.sweeps.size(); ++si) {
         const SweepHost& s = p.sweeps[si];
         for (int r = s.range_begin; r < s.range_end; ++r) {
             const uint32_t d0 = p.r_desc[2 * r], d1 = p.r_desc[2 * r + 1];
             for (uint32_t g = (d0 & 0xffffu); g < (d0 >> 16); ++g) {
                 const uint32_t h = p.g_hdr[2 * (s.group_begin + g)];
-                fprintf(f, "%zu,%d,%u,%u,%u,%u,%u,%u,%u,%llu\n", si, r - s.range_begin, (d1 >> RNG_KIND_SHIFT) & 3u, d1 >> RNG_SKIP_SHIFT, (d1 >> RNG_POL_SHIFT) & 1u, g,
-                        (h >> HDR_NT_SHIFT) & HDR_NT_MASK, h & HDR_XL_MASK, (h & HDR_IMAG) ? 1u : 0u, (unsigned long long)s.tile_mask);
+                fprintf(f, "%zu,%d,%u,%u,%u,%u,%u,%u,%u,%llu,%d\n", si, r - s.range_begin, (d1 >> RNG_KIND_SHIFT) & 3u, d1 >> RNG_SKIP_SHIFT, (d1 >> RNG_POL_SHIFT) & 1u, g,
+                        (h >> HDR_NT_SHIFT) & HDR_NT_MASK, h & HDR_XL_MASK, (h & HDR_IMAG) ? 1u : 0u, (unsigned long long)s.tile_mask, (int)p.classes[(size_t)s.cls].x_hi);
             }
         }
     }
