@@ -1102,6 +1102,408 @@ __global__ void __launch_bounds__(NT_MAX, 1) tile_expect_kernel(const __grid_con
     }
 }
 
+// ---- EXPECT kernel, second generation: control words in the constant bank ----------------------------------------------------------
+// Same tile layout, tile switch and arithmetic as tile_expect_kernel.  What changes is where a warp waits (ncu source view of the
+// kernels above, profiles/r02_expect_28q_source_notes.txt: the shared-memory pipe is the binding resource and runs at 77 % on a large
+// sweep, 63 % over the step; a LDS issued while it is busy returns after 300-1000 cycles, and the group loop took three such round
+// trips in a row -- range descriptor, group header, partner rows -- besides re-reading %tid and the shared window base per group):
+//   * range descriptors and group headers travel in the kernel parameter next to the term records (one record stream: header, terms,
+//     header, terms ...), so every control word is a constant-bank load with a warp-uniform index, not a shared-memory round trip;
+//   * the first eight partner rows of a group are requested BEFORE its term sum is formed (constant loads, popc, adds: no shared
+//     memory), the other eight while the first are consumed;
+//   * the term sums of KIND_RUNS groups are straight-line code for the common run lengths (a group of a weight-4 X mask is one run);
+//   * %tid and the shared window base are pinned in registers (opaque to the compiler, which otherwise re-reads the special
+//     registers inside the loops), partner rows are ld.shared at [register + immediate].
+constexpr int E2_MAX_RANGES = 48;
+constexpr int E2_MAX_REC = 2000;  // group headers + staged terms of one sweep
+
+struct Expect2Args {
+    const void* ket;
+    const void* bra;
+    double2* partials;
+    const uint64_t* nat_off;  // PLAN_TABLE entries each, see plan_host.h
+    const uint64_t* loc_off;
+    const uint32_t* nat_loc;
+    unsigned long long tile_begin, n_tiles;  // the launch covers tiles [tile_begin, n_tiles)
+    unsigned long long tile_stride;          // gridDim.x
+    unsigned long long ket_xor;
+    unsigned long long* prof;  // development: per-warp phase cycle counters (QFE_PROF=1), else null
+    int n_ranges, n_runs, same_tile, n_rec;
+    uint8_t run_pos[PLAN_MAX_RUNS];
+    uint8_t run_len[PLAN_MAX_RUNS];
+    // range ri: .x = record index of its first group header | number of groups << 16; .y = kind / polarity / skip bit as in r_desc
+    uint2 rng[E2_MAX_RANGES];
+    // group: one header record (.x = header word a of plan_host.h) followed by its staged terms (.x/.y = coefficient bits: double, or
+    // float in .x for complex64 states; .z = t_zl, .w = t_zoc)
+    uint4 rec[E2_MAX_REC];
+};
+static_assert(sizeof(Expect2Args) <= 32764, "kernel parameter space");
+
+// shared-memory accesses of the group loops by 32-bit shared address
+template <typename real_t> struct Smem;
+template <> struct Smem<double> {
+    static __device__ __forceinline__ double2 ld(const uint32_t addr) {
+        double2 v;
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+        return v;
+    }
+    static __device__ __forceinline__ void st(const uint32_t addr, const double2 v) {
+        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(v.x), "d"(v.y) : "memory");
+    }
+};
+template <> struct Smem<float> {
+    static __device__ __forceinline__ float2 ld(const uint32_t addr) {
+        float2 v;
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+        return v;
+    }
+    static __device__ __forceinline__ void st(const uint32_t addr, const float2 v) {
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
+    }
+};
+
+template <typename real_t> __device__ __forceinline__ real_t rec_coeff(const uint4& q);
+template <> __device__ __forceinline__ double rec_coeff<double>(const uint4& q) { return __hiloint2double((int)q.y, (int)q.x); }
+template <> __device__ __forceinline__ float rec_coeff<float>(const uint4& q) { return __uint_as_float(q.x); }
+
+// c_t (-1)^{|z_t & b|} of staged term record i for the thread's rows (jhi) on tile `tile`
+template <typename real_t>
+__device__ __forceinline__ real_t e2_term(const Expect2Args& a, const int i, const uint32_t jhi, const uint32_t tile) {
+    const uint4 q = a.rec[i];
+    return sign_by_parity(rec_coeff<real_t>(q), (uint32_t)__popc((q.z & jhi) ^ (q.w & tile)));
+}
+template <typename real_t, int N>
+__device__ __forceinline__ real_t e2_sum_fixed(const Expect2Args& a, const int t, const uint32_t jhi, const uint32_t tile) {
+    real_t c[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) c[i] = e2_term<real_t>(a, t + i, jhi, tile);  // all loads before the first use
+    real_t S0 = c[0], S1 = N > 1 ? c[1] : (real_t)0;
+#pragma unroll
+    for (int i = 2; i < N; ++i) {
+        if (i & 1)
+            S1 += c[i];
+        else
+            S0 += c[i];
+    }
+    return S0 + S1;
+}
+// signed sum of the n staged terms from record t on
+template <typename real_t>
+__device__ __forceinline__ real_t e2_sum(const Expect2Args& a, int t, const int n, const uint32_t jhi, const uint32_t tile) {
+    switch (n) {
+        case 1: return e2_sum_fixed<real_t, 1>(a, t, jhi, tile);
+        case 2: return e2_sum_fixed<real_t, 2>(a, t, jhi, tile);
+        case 3: return e2_sum_fixed<real_t, 3>(a, t, jhi, tile);
+        case 4: return e2_sum_fixed<real_t, 4>(a, t, jhi, tile);
+        case 5: return e2_sum_fixed<real_t, 5>(a, t, jhi, tile);
+        case 6: return e2_sum_fixed<real_t, 6>(a, t, jhi, tile);
+        default: break;
+    }
+    real_t S0 = (real_t)0, S1 = (real_t)0;
+    const int te = t + n;
+#pragma unroll 1
+    for (; t + 4 <= te; t += 4) {
+        const real_t c0 = e2_term<real_t>(a, t, jhi, tile), c1 = e2_term<real_t>(a, t + 1, jhi, tile);
+        const real_t c2 = e2_term<real_t>(a, t + 2, jhi, tile), c3 = e2_term<real_t>(a, t + 3, jhi, tile);
+        S0 += c0 + c2;
+        S1 += c1 + c3;
+    }
+#pragma unroll 1
+    for (; t < te; ++t) S0 += e2_term<real_t>(a, t, jhi, tile);
+    return S0 + S1;
+}
+
+// All groups of one range for the thread's 16 rows.  rp: record index of the first group header; sbase: shared address of the tile.
+template <typename real_t, int KIND, bool HALF, bool RE_ONLY>
+__device__ __forceinline__ void e2_range(const Expect2Args& a, int rp, const int ng, const uint32_t sbase, const uint32_t tid, const uint32_t jhi,
+                                         const uint32_t tile_no, const typename CplxOf<real_t>::type (&own)[R], double& e_re, double& e_im) {
+    using cplx_t = typename CplxOf<real_t>::type;
+    constexpr uint32_t ROWB = GeoExpect<real_t>::PLANE * (uint32_t)sizeof(cplx_t);  // bytes between the planes of two register rows
+    constexpr bool XROW = (KIND & KIND_XROW) != 0;
+    uint32_t hdr_next = a.rec[rp].x;
+#pragma unroll 1
+    for (int g = 0; g < ng; ++g) {
+        const uint32_t hdr = hdr_next;
+        const int nt = (int)((hdr >> HDR_NT_SHIFT) & HDR_NT_MASK);
+        const int t0 = rp + 1;
+        rp = t0 + nt;
+        hdr_next = a.rec[rp].x;  // the record after the last group of a sweep exists (zero): no bound to check
+        const bool imag = hdr & HDR_IMAG;
+        const uint32_t xr = hdr & (uint32_t)(R - 1);
+        // the partner thread's word of plane 0: thread index ^ thread bits of the X mask
+        const uint32_t paddr = sbase + (tid ^ ((hdr & HDR_XL_MASK) >> RB)) * (uint32_t)sizeof(cplx_t);
+        auto row_addr = [&](const int r) { return XROW ? paddr + (((uint32_t)r ^ xr) * ROWB) : paddr + (uint32_t)r * ROWB; };
+        cplx_t p[R];
+#pragma unroll
+        for (int r = 0; r < R / 2; ++r) p[r] = Smem<real_t>::ld(row_addr(r));  // travel while the term sum is formed
+        if (KIND == KIND_FAST) {
+            const real_t S = e2_sum<real_t>(a, t0, nt, jhi, tile_no);
+            if (HALF || RE_ONLY) {
+                // HALF: the pair (b, b^x) sums to 2 S (a a' + b b').  RE_ONLY: Re(Wc conj(own) p) = S Re(.) or, Wc = i S, -S Im(.)
+                const bool im = !HALF && imag;
+                real_t a0 = (real_t)0, a1 = (real_t)0, a2 = (real_t)0, a3 = (real_t)0;
+                if (!im) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        if (r < R / 2) p[r + R / 2] = Smem<real_t>::ld(row_addr(r + R / 2));
+                        if (r & 1) {
+                            a2 = fma(own[r].x, p[r].x, a2);
+                            a3 = fma(own[r].y, p[r].y, a3);
+                        } else {
+                            a0 = fma(own[r].x, p[r].x, a0);
+                            a1 = fma(own[r].y, p[r].y, a1);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        if (r < R / 2) p[r + R / 2] = Smem<real_t>::ld(row_addr(r + R / 2));
+                        if (r & 1) {
+                            a2 = fma(own[r].x, p[r].y, a2);
+                            a3 = fma(-own[r].y, p[r].x, a3);
+                        } else {
+                            a0 = fma(own[r].x, p[r].y, a0);
+                            a1 = fma(-own[r].y, p[r].x, a1);
+                        }
+                    }
+                }
+                const real_t s = (a0 + a1) + (a2 + a3);
+                if (HALF)
+                    e_re = fma((double)(S + S), (double)s, e_re);
+                else
+                    e_re = fma((double)(im ? -S : S), (double)s, e_re);
+            } else {
+                real_t a0 = (real_t)0, a1 = (real_t)0, b0 = (real_t)0, b1 = (real_t)0;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if (r < R / 2) p[r + R / 2] = Smem<real_t>::ld(row_addr(r + R / 2));
+                    a0 = fma(own[r].x, p[r].x, a0);  // Re conj(own) p = a a' + b b'
+                    a1 = fma(own[r].y, p[r].y, a1);
+                    b0 = fma(own[r].x, p[r].y, b0);  // Im conj(own) p = a b' - b a'
+                    b1 = fma(-own[r].y, p[r].x, b1);
+                }
+                real_t sr = a0 + a1, si = b0 + b1;
+                times_weight<real_t, false>(sr, si, S, (real_t)0, imag);
+                e_re += (double)sr;
+                e_im += (double)si;
+            }
+        } else if (HALF || RE_ONLY) {
+            // one real number per row, folded with the sign pattern of every run
+            const bool im = !HALF && imag;
+            int t = t0;
+            const int te = t0 + nt;
+            uint32_t head = a.rec[t].z;
+            int len = (int)(head >> TZ_RUN_SHIFT);
+            real_t S = e2_sum<real_t>(a, t, len, jhi, tile_no);  // first run: formed while the rows travel
+            real_t f[R];
+            if (!im) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if (r < R / 2) p[r + R / 2] = Smem<real_t>::ld(row_addr(r + R / 2));
+                    f[r] = fma(own[r].x, p[r].x, own[r].y * p[r].y);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if (r < R / 2) p[r + R / 2] = Smem<real_t>::ld(row_addr(r + R / 2));
+                    f[r] = fma(own[r].y, p[r].x, -own[r].x * p[r].y);  // -Im conj(own) p
+                }
+            }
+            real_t tot = S * fold_rows<real_t, R>(f, (head >> TZ_V_SHIFT) & 15u);
+            t += len;
+#pragma unroll 1
+            while (t < te) {
+                head = a.rec[t].z;
+                len = (int)(head >> TZ_RUN_SHIFT);
+                S = e2_sum<real_t>(a, t, len, jhi, tile_no);
+                t += len;
+                tot = fma(S, fold_rows<real_t, R>(f, (head >> TZ_V_SHIFT) & 15u), tot);
+            }
+            e_re += HALF ? (double)(tot + tot) : (double)tot;
+        } else {
+            // full complex value: rows in two chunks of 8 (keeps 16 products, not 32, live); the term sums of a run are formed per chunk
+            real_t tot_re = (real_t)0, tot_im = (real_t)0;
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                real_t fr[8], fi[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int r = 8 * ch + q;
+                    fr[q] = fma(own[r].x, p[q].x, own[r].y * p[q].y);
+                    fi[q] = fma(own[r].x, p[q].y, -own[r].y * p[q].x);
+                }
+                if (ch == 0) {  // the rows of the second chunk travel during the run loop of the first
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) p[q] = Smem<real_t>::ld(row_addr(8 + q));
+                }
+                int t = t0;
+                const int te = t0 + nt;
+#pragma unroll 1
+                while (t < te) {
+                    const uint32_t head = a.rec[t].z;
+                    const uint32_t v = (head >> TZ_V_SHIFT) & 15u;
+                    const int len = (int)(head >> TZ_RUN_SHIFT);
+                    const real_t S = e2_sum<real_t>(a, t, len, jhi, tile_no);
+                    t += len;
+                    real_t sr = fold_rows<real_t, 8>(fr, v), si = fold_rows<real_t, 8>(fi, v);
+                    if (ch) {
+                        const real_t s3 = sigma<real_t>(v, 3);
+                        sr *= s3;
+                        si *= s3;
+                    }
+                    times_weight<real_t, false>(sr, si, S, (real_t)0, imag);
+                    tot_re += sr;
+                    tot_im += si;
+                }
+            }
+            e_re += (double)tot_re;
+            e_im += (double)tot_im;
+        }
+    }
+}
+
+template <typename real_t, bool PROF, bool RE_ONLY>
+__global__ void __launch_bounds__(NT_MAX, 1) tile_expect2_kernel(const __grid_constant__ Expect2Args a) {
+    using G = GeoExpect<real_t>;
+    constexpr int NT = NT_MAX, NW = G::NW;
+    constexpr uint32_t PLANE = G::PLANE;
+    using cplx_t = typename CplxOf<real_t>::type;
+    constexpr uint32_t ROWB = PLANE * (uint32_t)sizeof(cplx_t);
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint64_t* s_nat_off = reinterpret_cast<uint64_t*>(smem + G::SM_NATOFF);
+    uint64_t* s_loc_off = reinterpret_cast<uint64_t*>(smem + G::SM_LOCOFF);
+    uint64_t* s_base = reinterpret_cast<uint64_t*>(smem + G::SM_BASE);
+    uint32_t* s_nat_loc = reinterpret_cast<uint32_t*>(smem + G::SM_NATLOC);
+    double2* s_red = reinterpret_cast<double2*>(smem + G::SM_RED);
+    unsigned long long* s_prof = reinterpret_cast<unsigned long long*>(smem + G::SM_PROF);
+    long long* s_tend = reinterpret_cast<long long*>(smem + G::SM_TEND);  // development counters, as in tile_sweep_kernel
+    long long t_gs = 0ll, t_end = 0ll, t_last = 0ll;
+    bool have_prev = false;
+
+    // %tid and the shared window base, opaque to the compiler: it keeps them in registers instead of re-reading the special registers
+    uint32_t tid, sbase = (uint32_t)__cvta_generic_to_shared(smem + G::SM_TILE);
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+    asm volatile("" : "+r"(sbase));
+    const int nR = a.n_ranges;
+    const cplx_t* __restrict__ ket = reinterpret_cast<const cplx_t*>(a.ket);
+    const cplx_t* __restrict__ bra = reinterpret_cast<const cplx_t*>(a.bra);
+
+    for (int i = (int)tid; i < PLAN_TABLE; i += NT) {
+        s_nat_off[i] = a.nat_off[i];
+        s_loc_off[i] = a.loc_off[i];
+        s_nat_loc[i] = a.nat_loc[i];
+    }
+    {
+        // entry (k, v): the 7 bits v of the tile number at bit 7k, deposited into the runs of the outer mask
+        unsigned long long rest = (unsigned long long)(tid & 127u) << (7 * (tid >> 7));
+        uint64_t b = 0;
+        for (int r = 0; r < a.n_runs; ++r) {
+            const int len = a.run_len[r];
+            b |= (rest & ((1ull << len) - 1ull)) << a.run_pos[r];
+            rest >>= len;
+        }
+        s_base[tid] = b;
+    }
+    if (PROF && tid < NW * PROF_PHASES) s_prof[tid] = 0ull;
+    __syncthreads();
+
+    const uint32_t jhi = tid << RB;
+    const uint32_t paddr0 = sbase + tid * (uint32_t)sizeof(cplx_t);  // the thread's word of plane 0
+    double e_re = 0.0, e_im = 0.0;
+    auto base_of = [&](const unsigned long long t) {  // tile numbers stay below 2^28 (shards of at most 2^40 amplitudes, plan_create)
+        return s_base[t & 127] | s_base[128 + ((t >> 7) & 127)] | s_base[256 + ((t >> 14) & 127)] | s_base[384 + ((t >> 21) & 127)];
+    };
+    // the thread's 16 amplitudes of a tile in natural order (idx = tid + u * NT: consecutive threads = consecutive amplitudes of a
+    // 128 B segment); the low 7 index bits are the thread's own
+    const uint64_t off_lo = s_nat_off[tid & 127u];
+    const uint32_t loc_lo = s_nat_loc[tid & 127u];
+    cplx_t v[R];
+    uint32_t vw[R];  // shared addresses of their words in the tile (the same for every tile; looked up per tile rather than held across the group loops)
+    auto request = [&](const unsigned long long t) {
+        const uint64_t kb = (base_of(t) ^ a.ket_xor) | off_lo;
+#pragma unroll
+        for (int u = 0; u < R; ++u) v[u] = ld_stream(ket + (kb | s_nat_off[128 + ((tid + u * NT) >> 7)]));
+#pragma unroll
+        for (int u = 0; u < R; ++u) vw[u] = sbase + tile_word<PLANE>(loc_lo | s_nat_loc[128 + ((tid + u * NT) >> 7)]) * (uint32_t)sizeof(cplx_t);
+    };
+
+    unsigned long long tile_id = a.tile_begin + blockIdx.x;
+    if (tile_id < a.n_tiles) request(tile_id);
+    for (; tile_id < a.n_tiles; tile_id += a.tile_stride) {
+        const unsigned long long next_id = tile_id + a.tile_stride;
+        __syncthreads();  // every partner row of the previous tile has been read
+        if (PROF && have_prev && (tid & 31u) == 0) {
+            t_last = s_tend[0];
+            for (int w = 1; w < NW; ++w) t_last = max(t_last, s_tend[w]);
+            s_prof[(tid >> 5) * PROF_PHASES + PH_SKEW] += (unsigned long long)(t_last - t_end);
+        }
+#pragma unroll
+        for (int u = 0; u < R; ++u) Smem<real_t>::st(vw[u], v[u]);
+        __syncthreads();
+        {
+            cplx_t own[R];
+            if (a.same_tile) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) own[r] = Smem<real_t>::ld(paddr0 + (uint32_t)r * ROWB);
+            } else {
+                const uint64_t base = base_of(tile_id);
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const uint32_t j = jhi | (uint32_t)r;
+                    own[r] = bra[base | s_loc_off[j & 127u] | s_loc_off[128 + (j >> 7)]];
+                }
+            }
+            if (PROF && (tid & 31u) == 0) {
+                t_gs = clock64();
+                if (have_prev) s_prof[(tid >> 5) * PROF_PHASES + PH_STAGE] += (unsigned long long)(t_gs - t_last);
+            }
+            const uint32_t tile_no = (uint32_t)tile_id;
+#pragma unroll 1
+            for (int ri = 0; ri < nR; ++ri) {
+                const uint2 d = a.rng[ri];
+                const uint32_t skipbit = d.y >> RNG_SKIP_SHIFT;
+                const bool half = a.same_tile && skipbit != 0;
+                // the row blocks (warps) of the other polarity hold the partners of these pairs
+                if (half && (((jhi >> skipbit) ^ (d.y >> RNG_POL_SHIFT)) & 1u)) continue;
+                const int rp = (int)(d.x & 0xffffu), ng = (int)(d.x >> 16);
+                const uint32_t kind = (d.y >> RNG_KIND_SHIFT) & 3u;
+                if (half) {
+                    if (kind == KIND_FAST)
+                        e2_range<real_t, KIND_FAST, true, RE_ONLY>(a, rp, ng, sbase, tid, jhi, tile_no, own, e_re, e_im);
+                    else if (kind == KIND_RUNS)
+                        e2_range<real_t, KIND_RUNS, true, RE_ONLY>(a, rp, ng, sbase, tid, jhi, tile_no, own, e_re, e_im);
+                    else
+                        e2_range<real_t, KIND_RUNS | KIND_XROW, true, RE_ONLY>(a, rp, ng, sbase, tid, jhi, tile_no, own, e_re, e_im);
+                } else {
+                    if (kind == KIND_FAST)
+                        e2_range<real_t, KIND_FAST, false, RE_ONLY>(a, rp, ng, sbase, tid, jhi, tile_no, own, e_re, e_im);
+                    else if (kind == KIND_RUNS)
+                        e2_range<real_t, KIND_RUNS, false, RE_ONLY>(a, rp, ng, sbase, tid, jhi, tile_no, own, e_re, e_im);
+                    else
+                        e2_range<real_t, KIND_RUNS | KIND_XROW, false, RE_ONLY>(a, rp, ng, sbase, tid, jhi, tile_no, own, e_re, e_im);
+                }
+            }
+        }
+        if (PROF && (tid & 31u) == 0) {
+            t_end = clock64();
+            s_prof[(tid >> 5) * PROF_PHASES + PH_GROUPS] += (unsigned long long)(t_end - t_gs);
+            s_prof[(tid >> 5) * PROF_PHASES + PH_ASYNC_TILES - 1] += 1ull;
+            s_prof[(tid >> 5) * PROF_PHASES + PH_ASYNC_TILES] += 1ull;  // marks the pipelined kernels in the counters
+            s_tend[tid >> 5] = t_end;
+            have_prev = true;
+        }
+        // the next tile's amplitudes (the CTA's last tile asks for its own again: unconditional, so the values stay in registers)
+        request(next_id < a.n_tiles ? next_id : tile_id);
+    }
+
+    double2 tot = block_reduce_sum(make_double2(e_re, e_im), s_red);
+    if (tid == 0) a.partials[blockIdx.x] = tot;
+    if (PROF && a.prof) {
+        __syncthreads();
+        if (tid < NW * PROF_PHASES) atomicAdd(a.prof + tid, s_prof[tid]);
+    }
+}
+
 // ---- pipelined APPLY kernel --------------------------------------------------------------------------------------------------------
 // y (+)= H|ket> for real-coefficient sweeps over full tiles: the group loops and the write-back through the tile of tile_sweep_kernel
 // <APPLY>, with the tile switch of tile_expect_kernel -- the next ket tile is requested as soon as the accumulators have left the
@@ -1450,6 +1852,71 @@ static int launch_expect_pipelined(qfe_ctx* ctx, SweepArgs& args, int grid, int 
     return dtype == QFE_C128 ? launch_expect_pipelined_p<double, false, false>(ctx, args, grid) : launch_expect_pipelined_p<float, false, false>(ctx, args, grid);
 }
 
+// second-generation EXPECT kernel (control words in the constant bank); QFE_EXPECT2=0 keeps the first generation
+static bool expect2_eligible(const SweepArgs& args) {
+    static const bool on = env_flag("QFE_EXPECT2", true);
+    return on && args.n_ranges <= E2_MAX_RANGES && args.n_terms + args.n_groups + 1 <= E2_MAX_REC;
+}
+static void fill_expect2_args(const qfe_plan* p, const SweepHost& s, const SweepArgs& a, Expect2Args& b) {
+    b.ket = a.ket;
+    b.bra = a.bra;
+    b.partials = a.partials;
+    b.nat_off = a.nat_off;
+    b.loc_off = a.loc_off;
+    b.nat_loc = a.nat_loc;
+    b.tile_begin = a.tile_begin;
+    b.n_tiles = a.n_tiles;
+    b.ket_xor = a.ket_xor;
+    b.prof = a.prof;
+    b.n_ranges = a.n_ranges;
+    b.n_runs = a.n_runs;
+    b.same_tile = a.same_tile;
+    memcpy(b.run_pos, a.run_pos, sizeof(b.run_pos));
+    memcpy(b.run_len, a.run_len, sizeof(b.run_len));
+    const PlanHost& h = p->h;
+    int rec = 0;
+    for (int r = 0; r < a.n_ranges; ++r) {
+        const uint32_t d0 = h.r_desc[2 * (size_t)(s.range_begin + r)], d1 = h.r_desc[2 * (size_t)(s.range_begin + r) + 1];
+        const uint32_t g0 = d0 & 0xffffu, g1 = d0 >> 16;
+        b.rng[r] = make_uint2((uint32_t)rec | ((g1 - g0) << 16), d1 & ~0xffffu);
+        for (uint32_t g = g0; g < g1; ++g) {
+            const uint32_t hdr = h.g_hdr[2 * (size_t)(s.group_begin + g)], t0 = h.g_hdr[2 * (size_t)(s.group_begin + g) + 1];
+            const uint32_t nt = (hdr >> HDR_NT_SHIFT) & HDR_NT_MASK;
+            b.rec[rec++] = make_uint4(hdr, 0u, 0u, 0u);
+            for (uint32_t t = t0; t < t0 + nt; ++t) {
+                const TermConst& q = a.tc[t];
+                b.rec[rec++] = make_uint4(q.c_lo, q.c_hi, q.zp, q.zoc);
+            }
+        }
+    }
+    b.rec[rec] = make_uint4(0u, 0u, 0u, 0u);  // the header prefetch of the last group reads one record past the end
+    b.n_rec = rec;
+}
+template <typename real_t, bool PROF, bool RE_ONLY>
+static int launch_expect2_p(qfe_ctx* ctx, Expect2Args& args, int grid) {
+    auto kern = tile_expect2_kernel<real_t, PROF, RE_ONLY>;
+    constexpr size_t smem = GeoExpect<real_t>::SM_TOTAL;
+    static int attr_device = -1;
+    if (attr_device != ctx->device) {
+        QFE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_device = ctx->device;
+    }
+    args.tile_stride = (unsigned long long)grid;
+    kern<<<grid, NT_MAX, smem, ctx->stream>>>(args);
+    ctx->launches++;
+    QFE_CUDA(cudaGetLastError());
+    return QFE_OK;
+}
+static int launch_expect2(qfe_ctx* ctx, const qfe_plan* p, const SweepHost& sw, SweepArgs& a, int grid, int dtype, bool real_only) {
+    if (prof_enabled()) QFE_TRY(prof_buffer(ctx, a));
+    static thread_local Expect2Args b;  // 32 KB: filled per launch, copied into the launch by the runtime
+    fill_expect2_args(p, sw, a, b);
+    if (prof_enabled()) return dtype == QFE_C128 ? launch_expect2_p<double, true, false>(ctx, b, grid) : launch_expect2_p<float, true, false>(ctx, b, grid);
+    if (real_only && !a.same_tile)  // (on the state's own tile the Hermitian half visit already forms the real part only)
+        return dtype == QFE_C128 ? launch_expect2_p<double, false, true>(ctx, b, grid) : launch_expect2_p<float, false, true>(ctx, b, grid);
+    return dtype == QFE_C128 ? launch_expect2_p<double, false, false>(ctx, b, grid) : launch_expect2_p<float, false, false>(ctx, b, grid);
+}
+
 template <typename real_t>
 static int launch_apply_pipelined_t(qfe_ctx* ctx, SweepArgs& args, int grid) {
     auto kern = tile_apply_kernel<real_t>;
@@ -1641,6 +2108,8 @@ static int run_class_reduce(qfe_ctx* ctx, const qfe_plan* p, int ci, const void*
             a.partials = ctx->partials.as<double2>() + (size_t)vpos * row;
             if (batch)
                 QFE_TRY(launch_tile_d<MODE_BATCH>(ctx, a, grid, sw.complex_w, dtype));
+            else if (pipelined_eligible(a, sw.complex_w) && expect2_eligible(a))
+                QFE_TRY(launch_expect2(ctx, p, sw, a, grid, dtype, real_only));
             else if (pipelined_eligible(a, sw.complex_w))
                 QFE_TRY(launch_expect_pipelined(ctx, a, grid, dtype, real_only));
             else
@@ -1841,7 +2310,10 @@ int qfe_expectation_class(qfe_ctx* ctx, const qfe_plan* p, int x_hi, const void*
 }
 
 int qfe_expectation_class_part(qfe_ctx* ctx, const qfe_plan* p, int x_hi, const void* bra, const void* ket, int dtype, int part, int n_parts, double* out) {
-    return expectation_class_part_impl(ctx, p, x_hi, bra, ket, dtype, part, n_parts, false, out);
+    // QFE_FORCE_REAL_ONLY=1 (development / tests): run the real-part-only kernels the sharded driver uses for its pair ranks, so that they can
+    // be checked on one GPU; the imaginary part of the result is then not meaningful
+    static const bool force_real = env_flag("QFE_FORCE_REAL_ONLY", false);
+    return expectation_class_part_impl(ctx, p, x_hi, bra, ket, dtype, part, n_parts, force_real, out);
 }
 
 }  // extern "C"
