@@ -448,7 +448,7 @@ def main():
     achieved = shard_bytes / avg_launch_s / 1e9
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(n_local, args.dtype),
-        "kernel": "tile_expect_async_kernel (real-coefficient EXPECT sweeps; tile_sweep_kernel<EXPECT> for the others)", "peak_source": peak_src,
+        "kernel": "tile_expect2_kernel (real-coefficient EXPECT sweeps over full tiles: every sweep of this workload)", "peak_source": peak_src,
         "bytes_per_launch": shard_bytes, "avg_launch_ms": 1e3 * avg_launch_s,
         "terms_per_sweep": T / max(sweeps_per_step, 1),
         "note": "each sweep evaluates terms_per_sweep Pauli terms per amplitude from one HBM pass, so the kernel is issue/shared-memory bound by design; "

@@ -321,6 +321,7 @@ int build_plan(const TermView& t, int n_local, int shard, const PlanLimits& lim,
                         if (pass == 0 ? touches_rows : (!touches_rows && !take.empty())) continue;  // pass 1 adds what pass 0 deferred
                         const int nt_padded = (groups[g].nt + 1) & ~1;  // staged term lists are padded to an even length
                         if ((int)take.size() >= lim.max_groups || nterms + nt_padded > lim.max_terms) break;
+                        if (lim.max_slots > 0 && !take.empty() && nterms + nt_padded + lim.group_overhead * ((int64_t)take.size() + 1) > lim.max_slots) break;
                         take.push_back(g);
                         nterms += nt_padded;
                     }

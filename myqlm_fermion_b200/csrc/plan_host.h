@@ -66,6 +66,8 @@ struct PlanLimits {
     int tile_bits = 13;
     int max_terms = 2048;  // per sweep (shared-memory staging capacity)
     int max_groups = 512;
+    int group_overhead = 0;  // staging slots a group costs besides its terms (1 when the group headers travel with the terms, sweep.cu)
+    int max_slots = 0;       // terms + group_overhead * groups of a sweep stay within this (0: no such bound)
     int fill_below = 32;   // a sweep with fewer groups also takes pending groups whose X mask touches its register positions
                            // (measured optimum at 28 qubits: 1.19 s against 1.22 s without, 1.21 s with 48)
 };

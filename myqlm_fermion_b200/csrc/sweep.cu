@@ -1439,7 +1439,15 @@ __global__ void __launch_bounds__(NT_MAX, 1) tile_expect2_kernel(const __grid_co
         }
 #pragma unroll
         for (int u = 0; u < R; ++u) Smem<real_t>::st(vw[u], v[u]);
+        if (PROF && have_prev && (tid & 31u) == 0) {  // [0]: last warp done -> this warp's amplitudes of the next tile have arrived and are stored
+            t_gs = clock64();
+            s_prof[(tid >> 5) * PROF_PHASES + PH_WAIT] += (unsigned long long)(t_gs - t_last);
+        }
         __syncthreads();
+        if (PROF && have_prev && (tid & 31u) == 0) {  // [1]: -> every warp has stored (barrier)
+            const long long t_b2 = clock64();
+            s_prof[(tid >> 5) * PROF_PHASES + PH_ISSUE] += (unsigned long long)(t_b2 - t_gs);
+        }
         {
             cplx_t own[R];
             if (a.same_tile) {
@@ -2108,7 +2116,7 @@ static int run_class_reduce(qfe_ctx* ctx, const qfe_plan* p, int ci, const void*
             a.partials = ctx->partials.as<double2>() + (size_t)vpos * row;
             if (batch)
                 QFE_TRY(launch_tile_d<MODE_BATCH>(ctx, a, grid, sw.complex_w, dtype));
-            else if (pipelined_eligible(a, sw.complex_w) && expect2_eligible(a))
+            else if (pipelined_eligible(a, sw.complex_w) && expect2_eligible(a) && (a.same_tile || real_only))  // (full complex visits: first generation)
                 QFE_TRY(launch_expect2(ctx, p, sw, a, grid, dtype, real_only));
             else if (pipelined_eligible(a, sw.complex_w))
                 QFE_TRY(launch_expect_pipelined(ctx, a, grid, dtype, real_only));
@@ -2195,6 +2203,10 @@ int qfe_plan_create(qfe_ctx* ctx, const qfe_terms* t, int n_local, int shard, in
     if (lim.tile_bits > 13) lim.tile_bits = 13;  // 2^13 complex128 amplitudes = 128 KB of the 227 KB shared memory
     lim.max_terms = sweep_max_terms(std::min(n_local, lim.tile_bits), p->batch);
     lim.max_groups = p->batch ? BATCH_MAX_GROUPS : SWEEP_MAX_GROUPS;
+    if (!p->batch) {  // every real-coefficient sweep over full tiles fits the record stream of tile_expect2_kernel (headers + terms + one pad)
+        lim.group_overhead = 1;
+        lim.max_slots = E2_MAX_REC - 1;
+    }
     p->lim = lim;
     p->hermitian = true;
     for (int64_t i = 0; i < t->T && p->hermitian; ++i) p->hermitian = t->c[2 * i + 1] == 0.0;

@@ -1,5 +1,9 @@
-"""Summarise an .ncu-rep (raw page) into the handful of metrics we track. usage: ncu_summary.py file.ncu-rep"""
-import csv, subprocess, sys
+"""Summarise an .ncu-rep (raw page) into the handful of metrics we track.
+usage: ncu_summary.py file.ncu-rep [--traffic n_local dtype]
+--traffic appends the capture's per-launch DRAM bytes (mean over the captured launches of the sweep kernel) to profiles/ncu_traffic.json,
+which bench.py reads for roofline.traffic."""
+import csv, json, subprocess, sys
+from pathlib import Path
 raw = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units = rows[0], rows[1]
@@ -18,3 +22,21 @@ for r in rows[2:]:
         if k in hdr:
             i = hdr.index(k)
             print(f"{k}: {r[i]} {units[i]}")
+
+if "--traffic" in sys.argv:
+    a = sys.argv.index("--traffic")
+    n_local, dtype = int(sys.argv[a + 1]), sys.argv[a + 2]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    def col(name):
+        i = hdr.index(name)
+        return [float(r[i].replace(",", "")) * scale[units[i]] for r in rows[2:]]
+    rd, wr, names = col('dram__bytes_read.sum'), col('dram__bytes_write.sum'), [r[hdr.index('Kernel Name')] for r in rows[2:]]
+    keep = [i for i in range(len(rd)) if rd[i] == rd[i] and wr[i] == wr[i]]  # ncu sometimes reports -nan for a replayed launch
+    rd, wr = [rd[i] for i in keep], [wr[i] for i in keep]
+    out = Path(__file__).resolve().parents[1] / "profiles" / "ncu_traffic.json"
+    doc = json.loads(out.read_text()) if out.exists() else {"captures": []}
+    doc["captures"] = [c for c in doc["captures"] if not (c["n_local"] == n_local and c["dtype"] == dtype)]
+    doc["captures"].append({"n_local": n_local, "dtype": dtype, "kernel": names[0].strip(), "launches": len(rd), "dram_bytes_read": sum(rd) / len(rd),
+                            "dram_bytes_write": sum(wr) / len(wr), "source": Path(sys.argv[1]).name})
+    out.write_text(json.dumps(doc, indent=1) + "\n")
+    print("wrote", out)
