@@ -1139,7 +1139,9 @@ struct Expect2Args {
 };
 static_assert(sizeof(Expect2Args) <= 32764, "kernel parameter space");
 
-// shared-memory accesses of the group loops by 32-bit shared address
+// shared-memory accesses to the tile by 32-bit shared address.  Every access to the tile in the kernels that use these is one of these
+// volatile statements: they keep their order among themselves and against the barriers; no "memory" clobber, so that the table lookups
+// (plain loads from regions that are never written after the prologue) can move across them.
 template <typename real_t> struct Smem;
 template <> struct Smem<double> {
     static __device__ __forceinline__ double2 ld(const uint32_t addr) {
@@ -1148,7 +1150,7 @@ template <> struct Smem<double> {
         return v;
     }
     static __device__ __forceinline__ void st(const uint32_t addr, const double2 v) {
-        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(v.x), "d"(v.y) : "memory");
+        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(v.x), "d"(v.y));
     }
 };
 template <> struct Smem<float> {
@@ -1158,7 +1160,7 @@ template <> struct Smem<float> {
         return v;
     }
     static __device__ __forceinline__ void st(const uint32_t addr, const float2 v) {
-        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y));
     }
 };
 
@@ -1190,15 +1192,13 @@ __device__ __forceinline__ real_t e2_sum_fixed(const Expect2Args& a, const int t
 // signed sum of the n staged terms from record t on
 template <typename real_t>
 __device__ __forceinline__ real_t e2_sum(const Expect2Args& a, int t, const int n, const uint32_t jhi, const uint32_t tile) {
-    switch (n) {
-        case 1: return e2_sum_fixed<real_t, 1>(a, t, jhi, tile);
-        case 2: return e2_sum_fixed<real_t, 2>(a, t, jhi, tile);
-        case 3: return e2_sum_fixed<real_t, 3>(a, t, jhi, tile);
-        case 4: return e2_sum_fixed<real_t, 4>(a, t, jhi, tile);
-        case 5: return e2_sum_fixed<real_t, 5>(a, t, jhi, tile);
-        case 6: return e2_sum_fixed<real_t, 6>(a, t, jhi, tile);
-        default: break;
-    }
+    // compare-and-branch in the order of frequency (weight-4 X masks carry 4, then 6 terms); a jump table costs an LDC + BRX round trip
+    if (n == 4) return e2_sum_fixed<real_t, 4>(a, t, jhi, tile);
+    if (n == 6) return e2_sum_fixed<real_t, 6>(a, t, jhi, tile);
+    if (n == 2) return e2_sum_fixed<real_t, 2>(a, t, jhi, tile);
+    if (n == 5) return e2_sum_fixed<real_t, 5>(a, t, jhi, tile);
+    if (n == 3) return e2_sum_fixed<real_t, 3>(a, t, jhi, tile);
+    if (n == 1) return e2_sum_fixed<real_t, 1>(a, t, jhi, tile);
     real_t S0 = (real_t)0, S1 = (real_t)0;
     const int te = t + n;
 #pragma unroll 1
@@ -1943,7 +1943,6 @@ static int launch_apply_pipelined_t(qfe_ctx* ctx, SweepArgs& args, int grid) {
 static int launch_apply_pipelined(qfe_ctx* ctx, SweepArgs& args, int grid, int dtype) {
     return dtype == QFE_C128 ? launch_apply_pipelined_t<double>(ctx, args, grid) : launch_apply_pipelined_t<float>(ctx, args, grid);
 }
-
 template <typename real_t, bool CPLX, int MODE>
 static int launch_tile(qfe_ctx* ctx, SweepArgs& args, int grid) {
     if constexpr (MODE == MODE_EXPECT && !CPLX && std::is_same<real_t, double>::value) {

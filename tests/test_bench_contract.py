@@ -44,8 +44,9 @@ def test_own_arm_line_has_the_contract_keys():
 
 
 def test_multi_gpu_lines_of_the_round():
-    """The 2- and 8-GPU lines (builder runs, short step counts): whole-job value, weak scaling, NCCL exchanges counted."""
-    one = _latest("r02_bench_1gpu_32q*.json")
+    """The 2- and 8-GPU lines (builder runs, short step counts): whole-job value, weak scaling, NCCL exchanges counted.  They are compared with the
+    1-GPU line of the same kernel generation (first-generation EXPECT kernel, before tile_expect2_kernel)."""
+    one = _latest("r02_bench_1gpu_32q_steps1.json")
     for pattern, n_gpus, n_qubits in (("r02_bench_2gpu_32q*.json", 2, 32), ("r02_bench_8gpu_34q*.json", 8, 34)):
         d = _latest(pattern)
         cfg = d["config"]
