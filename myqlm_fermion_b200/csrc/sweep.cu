@@ -1214,7 +1214,8 @@ __device__ __forceinline__ real_t e2_sum(const Expect2Args& a, int t, const int 
 }
 
 // All groups of one range for the thread's 16 rows.  rp: record index of the first group header; sbase: shared address of the tile.
-template <typename real_t, int KIND, bool HALF, bool RE_ONLY>
+// AHEAD: partner rows requested before the term sum is formed; every row that is consumed requests the row AHEAD further on.
+template <typename real_t, int KIND, bool HALF, bool RE_ONLY, int AHEAD = R / 2>
 __device__ __forceinline__ void e2_range(const Expect2Args& a, int rp, const int ng, const uint32_t sbase, const uint32_t tid, const uint32_t jhi,
                                          const uint32_t tile_no, const typename CplxOf<real_t>::type (&own)[R], double& e_re, double& e_im) {
     using cplx_t = typename CplxOf<real_t>::type;
@@ -1235,7 +1236,7 @@ __device__ __forceinline__ void e2_range(const Expect2Args& a, int rp, const int
         auto row_addr = [&](const int r) { return XROW ? paddr + (((uint32_t)r ^ xr) * ROWB) : paddr + (uint32_t)r * ROWB; };
         cplx_t p[R];
 #pragma unroll
-        for (int r = 0; r < R / 2; ++r) p[r] = Smem<real_t>::ld(row_addr(r));  // travel while the term sum is formed
+        for (int r = 0; r < AHEAD; ++r) p[r] = Smem<real_t>::ld(row_addr(r));  // travel while the term sum is formed
         if (KIND == KIND_FAST) {
             const real_t S = e2_sum<real_t>(a, t0, nt, jhi, tile_no);
             if (HALF || RE_ONLY) {
@@ -1245,7 +1246,7 @@ __device__ __forceinline__ void e2_range(const Expect2Args& a, int rp, const int
                 if (!im) {
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
-                        if (r < R / 2) p[r + R / 2] = Smem<real_t>::ld(row_addr(r + R / 2));
+                        if (r + AHEAD < R) p[r + AHEAD] = Smem<real_t>::ld(row_addr(r + AHEAD));
                         if (r & 1) {
                             a2 = fma(own[r].x, p[r].x, a2);
                             a3 = fma(own[r].y, p[r].y, a3);
@@ -1257,7 +1258,7 @@ __device__ __forceinline__ void e2_range(const Expect2Args& a, int rp, const int
                 } else {
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
-                        if (r < R / 2) p[r + R / 2] = Smem<real_t>::ld(row_addr(r + R / 2));
+                        if (r + AHEAD < R) p[r + AHEAD] = Smem<real_t>::ld(row_addr(r + AHEAD));
                         if (r & 1) {
                             a2 = fma(own[r].x, p[r].y, a2);
                             a3 = fma(-own[r].y, p[r].x, a3);
@@ -1276,7 +1277,7 @@ __device__ __forceinline__ void e2_range(const Expect2Args& a, int rp, const int
                 real_t a0 = (real_t)0, a1 = (real_t)0, b0 = (real_t)0, b1 = (real_t)0;
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    if (r < R / 2) p[r + R / 2] = Smem<real_t>::ld(row_addr(r + R / 2));
+                    if (r + AHEAD < R) p[r + AHEAD] = Smem<real_t>::ld(row_addr(r + AHEAD));
                     a0 = fma(own[r].x, p[r].x, a0);  // Re conj(own) p = a a' + b b'
                     a1 = fma(own[r].y, p[r].y, a1);
                     b0 = fma(own[r].x, p[r].y, b0);  // Im conj(own) p = a b' - b a'
@@ -1299,13 +1300,13 @@ __device__ __forceinline__ void e2_range(const Expect2Args& a, int rp, const int
             if (!im) {
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    if (r < R / 2) p[r + R / 2] = Smem<real_t>::ld(row_addr(r + R / 2));
+                    if (r + AHEAD < R) p[r + AHEAD] = Smem<real_t>::ld(row_addr(r + AHEAD));
                     f[r] = fma(own[r].x, p[r].x, own[r].y * p[r].y);
                 }
             } else {
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    if (r < R / 2) p[r + R / 2] = Smem<real_t>::ld(row_addr(r + R / 2));
+                    if (r + AHEAD < R) p[r + AHEAD] = Smem<real_t>::ld(row_addr(r + AHEAD));
                     f[r] = fma(own[r].y, p[r].x, -own[r].x * p[r].y);  // -Im conj(own) p
                 }
             }
@@ -1323,6 +1324,8 @@ __device__ __forceinline__ void e2_range(const Expect2Args& a, int rp, const int
         } else {
             // full complex value: rows in two chunks of 8 (keeps 16 products, not 32, live); the term sums of a run are formed per chunk
             real_t tot_re = (real_t)0, tot_im = (real_t)0;
+#pragma unroll
+            for (int r = AHEAD; r < R / 2; ++r) p[r] = Smem<real_t>::ld(row_addr(r));  // the first chunk is rows 0..7
 #pragma unroll
             for (int ch = 0; ch < 2; ++ch) {
                 real_t fr[8], fi[8];

@@ -1,6 +1,6 @@
-"""Development aid (one GPU): the second-generation EXPECT kernel (csrc/sweep.cu:tile_expect2_kernel) against the first (QFE_EXPECT2=0)
-on the same inputs -- <psi|H|psi>, the transition <phi|H|psi>, the real-part-only instance the sharded driver uses (QFE_FORCE_REAL_ONLY=1),
-complex128 and complex64, three encodings -- and their timings.  usage: python tools/check_expect2.py [M=11] [reps=3]"""
+"""Development aid (one GPU): a newer generation of the EXPECT kernel against the one before it (csrc/sweep.cu: tile_expect2_kernel against
+tile_expect_kernel with the knob QFE_EXPECT2, tile_expect3_kernel against tile_expect2_kernel with QFE_EXPECT3) on the same inputs -- <psi|H|psi>, the transition <phi|H|psi>, the real-part-only instance the sharded driver uses (QFE_FORCE_REAL_ONLY=1),
+complex128 and complex64, three encodings -- and their timings.  usage: python tools/check_expect2.py [M=11] [reps=3] [KNOB=QFE_EXPECT2]"""
 import json
 import os
 import subprocess
@@ -46,7 +46,7 @@ print("RESULT " + json.dumps(out))
 
 def run(env_extra, m, reps):
     env = dict(os.environ, **env_extra)
-    r = subprocess.run([sys.executable, "-c", CHILD % (str(ROOT), m, reps)], env=env, capture_output=True, text=True, timeout=1500)
+    r = subprocess.run([sys.executable, "-c", CHILD % (str(ROOT), m, reps)], env=env, capture_output=True, text=True, timeout=150)
     if r.returncode != 0:
         print(r.stderr[-3000:])
         raise SystemExit(1)
@@ -56,10 +56,11 @@ def run(env_extra, m, reps):
 def main():
     m = int(sys.argv[1]) if len(sys.argv) > 1 else 11
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-    old = run({"QFE_EXPECT2": "0"}, m, reps)
-    new = run({"QFE_EXPECT2": "1"}, m, reps)
-    old_r = run({"QFE_EXPECT2": "0", "QFE_FORCE_REAL_ONLY": "1"}, m, 1)
-    new_r = run({"QFE_EXPECT2": "1", "QFE_FORCE_REAL_ONLY": "1"}, m, 1)
+    knob = sys.argv[3] if len(sys.argv) > 3 else "QFE_EXPECT2"  # the kernel generation under test: knob=0 against knob=1
+    old = run({knob: "0"}, m, reps)
+    new = run({knob: "1"}, m, reps)
+    old_r = run({knob: "0", "QFE_FORCE_REAL_ONLY": "1"}, m, 1)
+    new_r = run({knob: "1", "QFE_FORCE_REAL_ONLY": "1"}, m, 1)
     ok = True
     for a, b, ar, br in zip(old, new, old_r, new_r):
         for name, tol in (("c128", 1e-11), ("c64", 2e-5)):
