@@ -522,4 +522,35 @@ int build_plan(const TermView& t, int n_local, int shard, const PlanLimits& lim,
     return 0;
 }
 
+void build_sweep_records(const PlanHost& p, const SweepHost& s, bool single_precision, SweepRecords& out) {
+    out.rng.clear();
+    out.rec.clear();
+    for (int32_t r = s.range_begin; r < s.range_end; ++r) {
+        const uint32_t d0 = p.r_desc[2 * (size_t)r], d1 = p.r_desc[2 * (size_t)r + 1];
+        const uint32_t g0 = d0 & 0xffffu, g1 = d0 >> 16;
+        out.rng.push_back((uint32_t)(out.rec.size() / 4) | ((g1 - g0) << 16));
+        out.rng.push_back(d1 & ~0xffffu);
+        for (uint32_t g = g0; g < g1; ++g) {
+            const uint32_t hdr = p.g_hdr[2 * (size_t)(s.group_begin + g)], t0 = p.g_hdr[2 * (size_t)(s.group_begin + g) + 1];
+            const uint32_t nt = (hdr >> HDR_NT_SHIFT) & HDR_NT_MASK;
+            out.rec.insert(out.rec.end(), {hdr, 0u, 0u, 0u});
+            for (uint32_t t = t0; t < t0 + nt; ++t) {
+                const size_t i = (size_t)s.term_begin + t;
+                uint32_t lo, hi = 0;
+                if (single_precision) {
+                    const float f = (float)p.t_cre[i];
+                    memcpy(&lo, &f, 4);
+                } else {
+                    uint64_t bits;
+                    memcpy(&bits, &p.t_cre[i], 8);
+                    lo = (uint32_t)bits;
+                    hi = (uint32_t)(bits >> 32);
+                }
+                out.rec.insert(out.rec.end(), {lo, hi, p.t_zl[i], p.t_zoc[i]});
+            }
+        }
+    }
+    out.rec.insert(out.rec.end(), {0u, 0u, 0u, 0u});
+}
+
 }  // namespace qfe

@@ -120,6 +120,18 @@ struct PlanHost {
     std::vector<int64_t> dg_begin;     // per direct group: first term (size n_dgroups+1)
 };
 
+// Record stream of ONE real-coefficient sweep, as tile_expect2_kernel reads it from its kernel parameter (sweep.cu, Expect2Args):
+//   rng: two words per range -- word 0 = record index of the first group header | number of groups << 16; word 1 = kind / polarity /
+//        skip bit as in r_desc (low 16 bits zero);
+//   rec: four words per record -- a group is one header record (word 0 = header word a) followed by its staged terms (words 0/1 =
+//        coefficient bits: a double, or a float in word 0 for complex64 states; word 2 = t_zl; word 3 = t_zoc); one all-zero record ends
+//        the stream (the kernel prefetches the header after the last group).
+struct SweepRecords {
+    std::vector<uint32_t> rng;
+    std::vector<uint32_t> rec;
+};
+void build_sweep_records(const PlanHost& p, const SweepHost& s, bool single_precision, SweepRecords& out);
+
 // returns 0 on success, nonzero with *err set otherwise
 int build_plan(const TermView& t, int n_local, int shard, const PlanLimits& lim, PlanHost& out, const char** err);
 

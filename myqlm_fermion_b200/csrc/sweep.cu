@@ -1868,7 +1868,7 @@ static bool expect2_eligible(const SweepArgs& args) {
     static const bool on = env_flag("QFE_EXPECT2", true);
     return on && args.n_ranges <= E2_MAX_RANGES && args.n_terms + args.n_groups + 1 <= E2_MAX_REC;
 }
-static void fill_expect2_args(const qfe_plan* p, const SweepHost& s, const SweepArgs& a, Expect2Args& b) {
+static void fill_expect2_args(const qfe_plan* p, const SweepHost& s, const SweepArgs& a, int dtype, Expect2Args& b) {
     b.ket = a.ket;
     b.bra = a.bra;
     b.partials = a.partials;
@@ -1884,24 +1884,12 @@ static void fill_expect2_args(const qfe_plan* p, const SweepHost& s, const Sweep
     b.same_tile = a.same_tile;
     memcpy(b.run_pos, a.run_pos, sizeof(b.run_pos));
     memcpy(b.run_len, a.run_len, sizeof(b.run_len));
-    const PlanHost& h = p->h;
-    int rec = 0;
-    for (int r = 0; r < a.n_ranges; ++r) {
-        const uint32_t d0 = h.r_desc[2 * (size_t)(s.range_begin + r)], d1 = h.r_desc[2 * (size_t)(s.range_begin + r) + 1];
-        const uint32_t g0 = d0 & 0xffffu, g1 = d0 >> 16;
-        b.rng[r] = make_uint2((uint32_t)rec | ((g1 - g0) << 16), d1 & ~0xffffu);
-        for (uint32_t g = g0; g < g1; ++g) {
-            const uint32_t hdr = h.g_hdr[2 * (size_t)(s.group_begin + g)], t0 = h.g_hdr[2 * (size_t)(s.group_begin + g) + 1];
-            const uint32_t nt = (hdr >> HDR_NT_SHIFT) & HDR_NT_MASK;
-            b.rec[rec++] = make_uint4(hdr, 0u, 0u, 0u);
-            for (uint32_t t = t0; t < t0 + nt; ++t) {
-                const TermConst& q = a.tc[t];
-                b.rec[rec++] = make_uint4(q.c_lo, q.c_hi, q.zp, q.zoc);
-            }
-        }
-    }
-    b.rec[rec] = make_uint4(0u, 0u, 0u, 0u);  // the header prefetch of the last group reads one record past the end
-    b.n_rec = rec;
+    // the record stream (plan_host.cpp: build_sweep_records, interpreted on the CPU by tests/csrc/plan_emul.cpp) goes into the parameter
+    static thread_local SweepRecords recs;
+    build_sweep_records(p->h, s, dtype != QFE_C128, recs);
+    memcpy(b.rng, recs.rng.data(), recs.rng.size() * sizeof(uint32_t));
+    memcpy(b.rec, recs.rec.data(), recs.rec.size() * sizeof(uint32_t));
+    b.n_rec = (int)(recs.rec.size() / 4) - 1;
 }
 template <typename real_t, bool PROF, bool RE_ONLY>
 static int launch_expect2_p(qfe_ctx* ctx, Expect2Args& args, int grid) {
@@ -1921,7 +1909,7 @@ static int launch_expect2_p(qfe_ctx* ctx, Expect2Args& args, int grid) {
 static int launch_expect2(qfe_ctx* ctx, const qfe_plan* p, const SweepHost& sw, SweepArgs& a, int grid, int dtype, bool real_only) {
     if (prof_enabled()) QFE_TRY(prof_buffer(ctx, a));
     static thread_local Expect2Args b;  // 32 KB: filled per launch, copied into the launch by the runtime
-    fill_expect2_args(p, sw, a, b);
+    fill_expect2_args(p, sw, a, dtype, b);
     if (prof_enabled()) return dtype == QFE_C128 ? launch_expect2_p<double, true, false>(ctx, b, grid) : launch_expect2_p<float, true, false>(ctx, b, grid);
     if (real_only && !a.same_tile)  // (on the state's own tile the Hermitian half visit already forms the real part only)
         return dtype == QFE_C128 ? launch_expect2_p<double, false, true>(ctx, b, grid) : launch_expect2_p<float, false, true>(ctx, b, grid);

@@ -3,6 +3,7 @@
 // in plain scalar complex128.  Lets the planner (coverage of the X masks by tile masks, tile geometry,
 // mask compression, coefficient folding) be checked on a machine without a GPU.  Not shipped, not
 // linked into libqfe.so.
+#include <algorithm>
 #include <complex>
 #include <cstdint>
 #include <cstdio>
@@ -238,5 +239,129 @@ extern "C" int plan_emul_dump(int n, int64_t T, const uint64_t* x, const uint64_
         }
     }
     fclose(f);
+    return 0;
+}
+
+// <bra|H_class|ket> of one x_hi class from the RECORD STREAMS of its sweeps (build_sweep_records), interpreted the way
+// tile_expect2_kernel walks them: range word -> (first record, group count, kind, polarity, skip bit); header record -> X mask, term
+// count, imaginary flag; term records -> coefficient bits, t_zl (lane / row-block z bits, register-row bits v, run length) and the outer z
+// bits packed against the tile number.  half_visit: Hermitian ranges count 2 Re over the rows whose skip bit equals the polarity.
+// single_precision: the coefficients travel as floats.  Returns 0, or a positive code naming the violated property; -1 if a sweep of the
+// class has complex coefficients or the register is split over operators (those do not take this path).
+extern "C" int plan_emul_run_records(int n, int64_t T, const uint64_t* x, const uint64_t* z, const double* c, int n_local, int shard, int tile_bits,
+                                     int max_terms, int max_groups, int max_slots, int x_hi, const double* bra_, const double* ket_, int half_visit,
+                                     int single_precision, double* out2, int64_t* stats /* sweeps, max records of a sweep, max ranges of a sweep */) {
+    std::vector<int32_t> owner((size_t)T, 0);
+    const double zero[2] = {0.0, 0.0};
+    TermView v;
+    v.n = n;
+    v.T = T;
+    v.x = x;
+    v.z = z;
+    v.c = c;
+    v.owner = owner.data();
+    v.n_slots = 1;
+    v.constant = zero;
+    PlanLimits lim;
+    lim.tile_bits = tile_bits;
+    lim.max_terms = max_terms;
+    lim.max_groups = max_groups;
+    lim.group_overhead = max_slots > 0 ? 1 : 0;
+    lim.max_slots = max_slots;
+    PlanHost p;
+    const char* err = nullptr;
+    if (build_plan(v, n_local, shard, lim, p, &err) != 0) return 1;
+    if (!p.use_tiles) return 2;
+    const cplx* bra = reinterpret_cast<const cplx*>(bra_);
+    const cplx* ket = reinterpret_cast<const cplx*>(ket_);
+    cplx out(0.0, 0.0);
+    stats[0] = stats[1] = stats[2] = 0;
+    SweepRecords recs;
+    for (const ClassHost& cls : p.classes) {
+        if (cls.x_hi != x_hi) continue;
+        for (int si = cls.sweep_begin; si < cls.sweep_end; ++si) {
+            const SweepHost& s = p.sweeps[si];
+            if (s.complex_w) return -1;
+            build_sweep_records(p, s, single_precision != 0, recs);
+            const int n_ranges = s.range_end - s.range_begin;
+            const int64_t n_rec = (int64_t)recs.rec.size() / 4;
+            stats[0]++;
+            stats[1] = std::max<int64_t>(stats[1], n_rec);
+            stats[2] = std::max<int64_t>(stats[2], n_ranges);
+            if ((int64_t)recs.rng.size() != 2 * (int64_t)n_ranges) return 3;
+            if (n_rec != (s.group_end - s.group_begin) + (s.term_end - s.term_begin) + 1) return 4;  // headers + terms + the closing record
+            if (max_slots > 0 && n_rec - 1 > max_slots && s.group_end - s.group_begin > 1) return 5;  // the planner's bound
+            for (int q = 0; q < 4; ++q)
+                if (recs.rec[4 * (n_rec - 1) + q] != 0u) return 6;
+            const uint32_t tile_amps = 1u << s.k;
+            std::vector<cplx> tile(tile_amps);
+            for (int64_t t = 0; t < s.n_tiles; ++t) {
+                const uint64_t base = tile_base(s, (uint64_t)t);
+                for (uint32_t j = 0; j < tile_amps; ++j) tile[j] = ket[(base ^ s.ket_xor) | tile_spread(s, j)];
+                const bool same = (bra == ket) && s.ket_xor == 0;
+                for (uint32_t j = 0; j < tile_amps; ++j) {
+                    const cplx own = bra[base | tile_spread(s, j)];
+                    const uint32_t jhi = j & ~15u, jr = j & 15u;
+                    int64_t next_rec = 0;
+                    for (int ri = 0; ri < n_ranges; ++ri) {
+                        const uint32_t d0 = recs.rng[2 * ri], d1 = recs.rng[2 * ri + 1];
+                        int64_t rp = d0 & 0xffffu;
+                        const int ng = (int)(d0 >> 16);
+                        if (rp != next_rec || (d1 & 0xffffu)) return 7;  // the ranges follow each other in the stream
+                        const uint32_t skipbit = d1 >> RNG_SKIP_SHIFT, pol = (d1 >> RNG_POL_SHIFT) & 1u, kind = (d1 >> RNG_KIND_SHIFT) & 3u;
+                        const bool half = same && half_visit && skipbit != 0;
+                        for (int g = 0; g < ng; ++g) {
+                            const uint32_t hdr = recs.rec[4 * rp];
+                            if (recs.rec[4 * rp + 1] | recs.rec[4 * rp + 2] | recs.rec[4 * rp + 3]) return 8;
+                            const uint32_t xl = hdr & HDR_XL_MASK;
+                            const int nt = (int)((hdr >> HDR_NT_SHIFT) & HDR_NT_MASK);
+                            const bool imag = hdr & HDR_IMAG;
+                            if (rp + 1 + nt >= n_rec) return 9;
+                            if (((kind & KIND_XROW) != 0) != ((xl & 15u) != 0)) return 10;
+                            double w = 0.0;
+                            int64_t tt = rp + 1;
+                            while (tt < rp + 1 + nt) {  // run by run, as the kernel does for KIND_RUNS; KIND_FAST is one run with v = 0
+                                const uint32_t head = recs.rec[4 * tt + 2];
+                                const uint32_t vrow = (head >> TZ_V_SHIFT) & 15u, len = head >> TZ_RUN_SHIFT;
+                                if (len == 0 || tt + len > rp + 1 + nt) return 11;
+                                if (kind == KIND_FAST && (vrow != 0 || (nt & 1))) return 12;
+                                double srun = 0.0;
+                                for (uint32_t q = 0; q < len; ++q) {
+                                    const uint32_t* r4 = &recs.rec[4 * (tt + q)];
+                                    double coeff;
+                                    if (single_precision) {
+                                        float f;
+                                        memcpy(&f, &r4[0], 4);
+                                        coeff = f;
+                                    } else {
+                                        const uint64_t bits = (uint64_t)r4[0] | ((uint64_t)r4[1] << 32);
+                                        memcpy(&coeff, &bits, 8);
+                                    }
+                                    // the kernel's parity: popc((t_zl & jhi) ^ (t_zoc & tile number)); the run fields of t_zl sit above bit 15
+                                    const int par = __builtin_popcount((r4[2] & jhi) ^ (r4[3] & (uint32_t)t)) & 1;
+                                    srun += par ? -coeff : coeff;
+                                }
+                                w += (__builtin_popcount(vrow & jr) & 1) ? -srun : srun;
+                                tt += len;
+                            }
+                            const cplx wc = imag ? cplx(0.0, w) : cplx(w, 0.0);
+                            const cplx contrib = std::conj(own) * wc * tile[j ^ xl];
+                            if (half) {
+                                if (imag || (31 - __builtin_clz(xl)) != (int)skipbit) return 13;
+                                if (((j >> skipbit) & 1u) == pol) out += 2.0 * std::real(contrib);
+                            } else {
+                                out += contrib;
+                            }
+                            rp += 1 + nt;
+                        }
+                        next_rec = rp;
+                    }
+                    if (next_rec != n_rec - 1) return 14;
+                }
+            }
+        }
+    }
+    out2[0] = out.real();
+    out2[1] = out.imag();
     return 0;
 }

@@ -224,3 +224,68 @@ def test_random_plans_property(emul):
         assert np.max(np.abs(phi - want_phi)) <= 1e-10
 
     run()
+
+
+def _run_records(lib, n, x, z, c, n_local, shard, tile_bits, x_hi, bra, ket, half_visit, single_precision=0, max_terms=1920, max_groups=512, max_slots=1999):
+    P = C.POINTER
+    lib.plan_emul_run_records.restype = C.c_int
+    lib.plan_emul_run_records.argtypes = [C.c_int, C.c_int64, P(C.c_uint64), P(C.c_uint64), P(C.c_double), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.c_int, P(C.c_double), P(C.c_double), C.c_int, C.c_int, P(C.c_double), P(C.c_int64)]
+    x = np.ascontiguousarray(x, dtype=np.uint64)
+    z = np.ascontiguousarray(z, dtype=np.uint64)
+    c = np.ascontiguousarray(c, dtype=np.complex128)
+    bra, ket = np.ascontiguousarray(bra), np.ascontiguousarray(ket)
+    out, stats = np.zeros(2), np.zeros(3, dtype=np.int64)
+    f64 = lambda a: a.view(np.float64).ctypes.data_as(P(C.c_double))
+    # bra is ket (the same buffer) when the caller passes the same array: the interpreter's half visit keys on that, like the kernel's same_tile
+    rc = lib.plan_emul_run_records(n, len(x), x.ctypes.data_as(P(C.c_uint64)), z.ctypes.data_as(P(C.c_uint64)), f64(c), n_local, shard, tile_bits, max_terms,
+                                   max_groups, max_slots, x_hi, f64(ket) if bra is ket else f64(bra), f64(ket), half_visit, single_precision,
+                                   out.ctypes.data_as(P(C.c_double)), stats.ctypes.data_as(P(C.c_int64)))
+    assert rc == 0, f"plan_emul_run_records failed with code {rc}"
+    return complex(out[0], out[1]), stats
+
+
+@pytest.mark.parametrize("enc", ["jordan-wigner", "bravyi-kitaev", "parity"])
+def test_record_stream_of_the_second_generation_expect_kernel(emul, enc):
+    """The record stream tile_expect2_kernel reads from its kernel parameter (plan_host.cpp: build_sweep_records -- range words, one header
+    record per group followed by its term records, a closing zero record) interpreted on the CPU the way the kernel walks it: <psi|H|psi>
+    with the Hermitian half visit, the transition <phi|H|psi> with full visits, and single-precision coefficients."""
+    n = 12
+    x, z, c, k = _molecule(6, enc, constant=0.0)
+    nz = (x != 0) | (z != 0)
+    x, z, c = x[nz], z[nz], c[nz]
+    psi, phi = _state(n, 0), _state(n, 1)
+    h_psi = spin.apply_packed(n, x, z, c, 0.0, psi)
+    want_e, want_t = np.vdot(psi, h_psi), np.vdot(phi, h_psi)
+    for tile_bits in (9, 11):
+        e, stats = _run_records(emul, n, x, z, c, n, 0, tile_bits, 0, psi, psi, half_visit=1)
+        assert abs(e - want_e.real) <= 1e-12 * abs(want_e)  # (the full visits of the groups without a row-block X bit leave rounding in Im)
+        t, _ = _run_records(emul, n, x, z, c, n, 0, tile_bits, 0, phi, psi, half_visit=1)  # another bra: no half visit whatever the flag says
+        assert abs(t - want_t) <= 1e-12 * abs(want_e)
+        e32, _ = _run_records(emul, n, x, z, c, n, 0, tile_bits, 0, psi, psi, half_visit=1, single_precision=1)
+        assert abs(e32 - want_e.real) <= 1e-6 * abs(want_e) and e32 != e
+        assert stats[0] >= 1 and stats[2] <= 48
+    # sharded: the classes of a register split over 4 ranks recombine (the pair ranks' split of a class is host logic, tests/test_sharded_gloo.py)
+    n_local, total = 10, 0.0
+    for r in range(4):
+        for x_hi in range(4):
+            own = psi[r << n_local : (r + 1) << n_local]
+            partner = own if x_hi == 0 else psi[(r ^ x_hi) << n_local : ((r ^ x_hi) + 1) << n_local]
+            v, _ = _run_records(emul, n, x, z, c, n_local, r, 9, x_hi, own, partner, half_visit=1)
+            total += v
+    assert abs(total - want_e) <= 1e-12 * abs(want_e)
+
+
+def test_planner_keeps_headers_plus_terms_within_the_record_capacity(emul):
+    """max_slots: terms + one header per group of a sweep stay within the record stream of the kernel parameter (the interpreter returns
+    code 5 otherwise); with a tight bound the plan needs more sweeps but gives the same number."""
+    n = 12
+    x, z, c, k = _molecule(6, "jordan-wigner")
+    nz = (x != 0) | (z != 0)
+    x, z, c = x[nz], z[nz], c[nz]
+    psi = _state(n, 4)
+    want = np.vdot(psi, spin.apply_packed(n, x, z, c, 0.0, psi)).real
+    loose, s_loose = _run_records(emul, n, x, z, c, n, 0, 10, 0, psi, psi, 1, max_slots=1999)
+    tight, s_tight = _run_records(emul, n, x, z, c, n, 0, 10, 0, psi, psi, 1, max_slots=120)
+    assert abs(loose - want) <= 1e-12 * abs(want) and abs(tight - want) <= 1e-12 * abs(want)
+    assert s_tight[0] > s_loose[0] and s_tight[1] - 1 <= 120 < s_loose[1]
