@@ -24,6 +24,7 @@ struct GramArgs {
     const void* bra[GP];
     const void* ket[GP];
     int nb, nk;
+    int diag;  // the bras ARE the kets (diagonal panel of a Hermitian Gram matrix): only the 4 x 4 blocks on and above the diagonal are formed
     long long n_chunks;
     double2* partials;  // [entry (i * GP + j)][CTA]
 };
@@ -37,7 +38,22 @@ __global__ void __launch_bounds__(256) gram_panel_kernel(const __grid_constant__
     using cplx_t = typename G2<real_t>::type;
     __shared__ double2 s[GC * GROW];  // amplitude-major: word (amp, v) at amp * GROW + v
     const int tid = threadIdx.x;
-    const int bi = tid >> 5, bj = (tid & 31) >> 2, sub = tid & 3;
+    // entry block (bi, bj) of 4 x 4 entries, amplitudes sub, sub + 4, ... of every chunk.  A diagonal panel has 36 blocks with bi <= bj
+    // (row-major over the upper triangle): 144 of the 256 threads accumulate (the kernel is FP64-bound), all of them load.
+    int bi = tid >> 5, bj = (tid & 31) >> 2;
+    const int sub = tid & 3;
+    bool active = true;
+    if (a.diag) {
+        int rem = tid >> 2;
+        active = rem < 36;
+        bi = 0;
+        while (active && rem >= 8 - bi) {
+            rem -= 8 - bi;
+            ++bi;
+        }
+        bj = active ? bi + rem : 0;
+        if (!active) bi = 0;
+    }
     // loader role: element e = tid + 256 u is amplitude (e & 31) of vector (e >> 5): a warp reads 32 consecutive amplitudes of one vector
     const cplx_t* src[8];
 #pragma unroll
@@ -70,6 +86,7 @@ __global__ void __launch_bounds__(256) gram_panel_kernel(const __grid_constant__
         for (int u = 0; u < 8; ++u) s[(tid & 31) * GROW + ((tid + 256 * u) >> 5)] = make_double2((double)nxt[u].x, (double)nxt[u].y);
         __syncthreads();
         if (chunk + gridDim.x < a.n_chunks) fetch(chunk + gridDim.x);
+        if (active)
 #pragma unroll 2
         for (int amp = sub; amp < GC; amp += 4) {
             const double2* row = s + amp * GROW;
@@ -98,7 +115,7 @@ __global__ void __launch_bounds__(256) gram_panel_kernel(const __grid_constant__
             i += __shfl_xor_sync(0xffffffffu, i, 1);
             r += __shfl_xor_sync(0xffffffffu, r, 2);
             i += __shfl_xor_sync(0xffffffffu, i, 2);
-            if (sub == 0) a.partials[(size_t)((4 * bi + q) * GP + 4 * bj + l) * gridDim.x + blockIdx.x] = make_double2(r, i);
+            if (active && sub == 0) a.partials[(size_t)((4 * bi + q) * GP + 4 * bj + l) * gridDim.x + blockIdx.x] = make_double2(r, i);
         }
 }
 
@@ -136,6 +153,7 @@ int qfe_vec_gram(qfe_ctx* ctx, const void* const* bras, int nb, const void* cons
             a.nk = std::min(GP, nk - j0);
             for (int i = 0; i < a.nb; ++i) a.bra[i] = bras[i0 + i];
             for (int j = 0; j < a.nk; ++j) a.ket[j] = kets[j0 + j];
+            a.diag = (symmetric && j0 == i0) ? 1 : 0;  // (the host reads the upper triangle of such a panel only; the rest of the partials is unspecified)
             a.n_chunks = n_chunks;
             a.partials = ctx->partials.as<double2>();
             if (dtype == QFE_C128)
