@@ -19,6 +19,11 @@
 //   * a shard with fewer tiles than SMs is worked on by up to 16 CTAs per tile, each with a slice of the groups of every range;
 //   * qfe_expectation_host / qfe_expectation_class0_host upload the state on a second stream in 16 pieces and run the first sweeps
 //     piece by piece behind the copy.
+// Kernels: tile_sweep_kernel (generic: EXPECT / APPLY / BATCH, complex coefficients, small tiles, tiles shared by several CTAs) and, for
+// real-coefficient sweeps over full 2^13-amplitude tiles, tile_expect2_kernel (<bra|H|ket>: control words in the constant bank, the
+// dominant kernel of the bench), tile_expect_kernel (its predecessor: full complex transition values, QFE_EXPECT2=0) and
+// tile_apply_kernel (y (+)= H|ket>); direct_kernel for shards smaller than a tile and as a cross-check.  DESIGN.md section 4 has the
+// measurements behind each of them and the variants that were built and not kept.
 // No tensor cores: this is an XOR-gather with +-1 weights, not a dense contraction.
 #include <algorithm>
 #include <cstdlib>
