@@ -1,5 +1,5 @@
 """Development aid (one GPU): a newer generation of the EXPECT kernel against the one before it (csrc/sweep.cu: tile_expect2_kernel against
-tile_expect_kernel with the knob QFE_EXPECT2, tile_expect3_kernel against tile_expect2_kernel with QFE_EXPECT3) on the same inputs -- <psi|H|psi>, the transition <phi|H|psi>, the real-part-only instance the sharded driver uses (QFE_FORCE_REAL_ONLY=1),
+tile_expect_kernel with the knob QFE_EXPECT2; any other on/off knob of the library can be named) on the same inputs -- <psi|H|psi>, the transition <phi|H|psi>, the real-part-only instance the sharded driver uses (QFE_FORCE_REAL_ONLY=1),
 complex128 and complex64, three encodings -- and their timings.  usage: python tools/check_expect2.py [M=11] [reps=3] [KNOB=QFE_EXPECT2]"""
 import json
 import os

@@ -1,6 +1,6 @@
 """Development aid: time <psi|H|psi> of the synthetic molecular JW Hamiltonian at n = 2M qubits and, with QFE_PROF=1 in the
 environment, print where the warps of the sweep kernel spend their cycles (phases of the tile loop, summed over CTAs and sweeps).
-usage: [QFE_ASYNC=0|1] [QFE_PROF=1] python tools/phase_prof.py M [reps]"""
+usage: [QFE_EXPECT2=0|1] [QFE_PIPELINED=0|1] [QFE_PROF=1] python tools/phase_prof.py M [reps] [transition]"""
 import ctypes as C
 import json
 import os

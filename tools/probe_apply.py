@@ -1,5 +1,5 @@
 """Quick timing probe (one GPU, development): H|psi> and <psi|H|psi> of the synthetic molecular JW Hamiltonian at n = 2M qubits and H|psi> of the
-n-qubit Hubbard chain (the Lanczos matvec), CUDA events on the launching stream.  usage: [QFE_APPLY2=0|1|2] python tools/probe_apply.py M [reps] [hubbard]"""
+n-qubit Hubbard chain (the Lanczos matvec), CUDA events on the launching stream.  usage: python tools/probe_apply.py M [reps] [hubbard]"""
 import json
 import os
 import sys
